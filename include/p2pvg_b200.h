@@ -1,0 +1,126 @@
+/* p2pvg_b200 — C ABI of the sm_100a kernels behind the p2pvg training hot path.
+ *
+ * The reference (yccyenchicheng/p2pvg) has no FFI of its own: its boundary for this path is the Python
+ * module API (models/p2p_model.py, models/lstm.py, models/dcgan_64.py, models/dcgan_128.py,
+ * misc/criterion.py).  The drop-in Python modules in p2pvg_b200/ keep that API and call the entry
+ * points below through ctypes.  Each entry point cites the reference lines whose arithmetic it
+ * replaces.  Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - the caller (PyTorch) owns every buffer; the library allocates nothing persistent;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative P2PVG_ERR_* code otherwise; p2pvg_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback: unsupported shapes are errors.
+ *   - dtype: 0 = fp32, 1 = bf16 ("act dtype" of the conv stacks); statistics/LSTM/optimizer are fp32.
+ *   - activations are NHWC, flattened to [rows, C]; a "group" is one encoder/decoder call of the
+ *     reference (BatchNorm statistics are per group).
+ */
+#ifndef P2PVG_B200_H
+#define P2PVG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2PVG_OK 0
+#define P2PVG_ERR_BAD_ARG -1
+#define P2PVG_ERR_UNSUPPORTED -2
+#define P2PVG_ERR_CUDA -3
+#define P2PVG_ERR_WORKSPACE -4
+
+#define P2PVG_F32 0
+#define P2PVG_BF16 1
+
+#define P2PVG_ACT_NONE 0
+#define P2PVG_ACT_LRELU 1 /* LeakyReLU(0.2): models/dcgan_64.py:10,22 */
+#define P2PVG_ACT_TANH 2  /* models/dcgan_64.py:45, models/lstm.py:18 */
+
+int p2pvg_version(void);
+const char* p2pvg_last_error(void);
+/* 1 when the tcgen05/TMA GEMM can be used on this process' device (driver entry points resolved). */
+int p2pvg_has_tcgen05(void);
+/* 0 = pick automatically (tcgen05 for bf16 operands), 1 = force the CUDA-core GEMM, 2 = force tcgen05 */
+int p2pvg_set_gemm_impl(int impl);
+
+/* C[M,N] = (accumulate ? C : 0) + opA(A)*opB(B) + bias[n] + addend[m,n]
+ *   a_mn=0: A[m*lda+k] (K-major), a_mn=1: A[k*lda+m];  b_mn=0: B[n*ldb+k], b_mn=1: B[k*ldb+n].
+ * Replaces the library GEMMs behind nn.Conv2d / nn.ConvTranspose2d (models/dcgan_64.py:8,20,43,64,76 after
+ * lowering), nn.Linear and nn.LSTMCell (models/lstm.py:13-17,54-57) and their autograd backward.
+ * bf16 operands run on tcgen05 tensor cores (fp32 accumulation in TMEM); fp32 operands on CUDA cores.
+ * workspace: split-K partials for the tensor-core path (may be NULL when ws_bytes == 0). */
+int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int c_dtype,
+               int64_t ldc, int M, int N, int K, int accumulate, const float* bias, const void* addend, int64_t ldd,
+               void* workspace, size_t ws_bytes, void* stream);
+
+/* 4x4 / stride 2 / pad 1 lowering (nn.Conv2d(nin,nout,4,2,1), models/dcgan_64.py:8; and the data-gradient of
+ * nn.ConvTranspose2d(nin,nout,4,2,1), models/dcgan_64.py:20): x [N,H,W,C] -> col [N*H/2*W/2, 16*C], K order (kh,kw,c). */
+int p2pvg_im2col_k4s2p1(const void* x, void* col, int dtype, int N, int H, int W, int C, void* stream);
+/* Inverse gather (ConvTranspose2d forward after the GEMM, Conv2d data-gradient): y [N,2Hi,2Wi,C] from
+ * col [N*Hi*Wi,16*C]; optional second operand col2 holds the skip-connection half of torch.cat([d, skip], 1)
+ * (models/dcgan_64.py:84-87) computed once per distinct source call: image n reads col2 image
+ * grp_src[n / imgs_per_group]*imgs_per_group + n % imgs_per_group. */
+int p2pvg_col2im_k4s2p1(const void* col, const void* col2, const int* grp_src, int imgs_per_group, void* y, int dtype, int N,
+                        int Hi, int Wi, int C, const float* bias, int accumulate, void* stream);
+/* dst (contiguous, dims[4]) = src gathered with per-destination-dimension strides (weight packing, NCHW->NHWC, casts). */
+int p2pvg_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims /*host*/,
+                   const int64_t* src_strides /*host*/, int accumulate, void* stream);
+int p2pvg_add_indexed(void* dst, const void* src, int dtype, const int* dst_idx, int F, int64_t n, void* stream);
+int p2pvg_group_sum(const void* in, void* out, int dtype, const int* grp_src, int G, int F, int64_t n, void* stream);
+
+/* nn.BatchNorm2d in training mode (models/dcgan_64.py:9,21,44,65), statistics per group. */
+size_t p2pvg_bn_workspace_bytes(int G, int C);
+int p2pvg_bn_fwd_stats(const void* x, int dtype, int G, int64_t R, int C, const float* gamma, const float* beta, float eps,
+                       void* ws, size_t ws_bytes, float* mean, float* invstd, float* var_unbiased, float* scale, float* shift,
+                       void* stream);
+int p2pvg_bn_act(const void* x, void* y, int dtype, const float* scale, const float* shift, int G, int64_t R, int C, int act,
+                 void* stream);
+int p2pvg_bn_bwd(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
+                 const float* gamma, int G, int64_t R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
+                 float* sum_dzx, void* stream);
+int p2pvg_bn_param_grad(const float* sum_dz, const float* sum_dzx, int G, int C, float* dgamma, float* dbeta, void* stream);
+/* running_mean / running_var EMA applied call by call in the reference's call order. */
+int p2pvg_bn_ema(float* rmean, float* rvar, const float* mean, const float* var_unbiased, const int* order, int ncalls, int C,
+                 float momentum, void* stream);
+
+/* nn.LSTMCell pointwise part (models/lstm.py:41,89): gates [B,4R] in: pre-activations (i,f,g,o), out: activations. */
+int p2pvg_lstm_pointwise_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, int B, int R, void* stream);
+int p2pvg_lstm_pointwise_bwd(const float* dh, const float* dc_next, const float* gates, const float* c_prev, const float* c,
+                             float* dgates, float* dc_prev, int B, int R, void* stream);
+/* gaussian_lstm.reparameterize (models/lstm.py:76-81) for posterior and prior + KLCriterion.forward
+ * (misc/criterion.py:10-15) summed over all elements (division by opt.batch_size happens in finalize_losses). */
+int p2pvg_reparam_kl_fwd(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,
+                         const float* eps_p, float* z, float* z_p, int n, float* kl_sum, void* stream);
+int p2pvg_reparam_kl_bwd(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,
+                         const float* eps_p, const float* dz, const float* dz_p, float kl_coef, float* dmu, float* dlv,
+                         float* dmu_p, float* dlv_p, int n, void* stream);
+/* torch.cat([h, global_z | z, time_until_cp, delta_time], 1) (models/p2p_model.py:241-242,247,252) for all steps. */
+int p2pvg_build_concat(float* dst, const float* A, const int* ia, int ga, const float* Bm, const int* ib, int gb,
+                       const float* tuc, const float* dt, int S, int B, void* stream);
+int p2pvg_gather_add_cols(float* dst, const float* src, const int* idx, int S, int T, int B, int g, int W, int col0, int init,
+                          void* stream);
+/* align_loss += MSE(h[0], h_pred) with h[0] = batch row 0 broadcast (models/p2p_model.py:224-225), value + gradients. */
+int p2pvg_align(const float* H, const int* in_idx, const float* h_pred, int P, int B, int g, float coef, float* loss_partial,
+                float* d_hpred, float* dH, void* stream);
+/* out[c] (+)= sum_r x[r*ld + c] — bias gradients. */
+int p2pvg_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* out, int accumulate, void* stream);
+int p2pvg_act_fwd(float* x, int64_t n, int act, void* stream);
+int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
+
+/* nn.Sigmoid (models/dcgan_64.py:77) + nn.MSELoss (models/p2p_model.py:254,256): per-group sum of squared error
+ * partials [G, p2pvg_mse_chunks()] and d(loss)/d(raw) = coef[g]*2*(s-x)*s*(1-s). */
+int p2pvg_mse_chunks(void);
+int p2pvg_sigmoid_mse(const void* raw, int dtype, const float* x, const int* tgt, const float* coef, int G, int64_t E,
+                      void* pred, void* d_raw, float* partial, void* stream);
+/* the four scalars returned by P2PModel.forward (models/p2p_model.py:271): out[0..3] = mse,kld,cpc,align (/seq_len). */
+int p2pvg_finalize_losses(const float* mse_partial, int n_recon, int has_cpc, double E, const float* kl_sum, float batch_size,
+                          const float* align_partial, int n_align, float seq_len, float* out, void* stream);
+/* optim.Adam.step of PyTorch 1.0 (README.md:62; models/p2p_model.py:273-280) on a flat parameter arena. */
+int p2pvg_adam_legacy(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                      double eps, const int* step_ptr, void* stream);
+int p2pvg_scale(float* x, int64_t n, float a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,211 @@
+"""ctypes binding of libp2pvg_b200.so (C ABI declared in include/p2pvg_b200.h).
+
+``CudaKernels`` is the kernel backend the engine talks to.  There is no CPU / PyTorch fallback: if the
+shared library is missing the import of the product path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp2pvg_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+
+_lib = None
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(p2pvg_b200 has no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.p2pvg_last_error.restype = ctypes.c_char_p
+        _lib.p2pvg_bn_workspace_bytes.restype = ctypes.c_size_t
+    return _lib
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_f = ctypes.c_float
+_d = ctypes.c_double
+_sz = ctypes.c_size_t
+
+
+def _p(t):
+    if t is None:
+        return _vp(0)
+    return _vp(t.data_ptr())
+
+
+class CudaKernels:
+    """Launches the sm_100a kernels on the current torch CUDA stream."""
+
+    name = "cuda"
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("p2pvg_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else "cuda")
+        self._gemm_ws = None
+        self._bn_ws = None
+        self.launches = 0
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _stream(self):
+        return _vp(torch.cuda.current_stream().cuda_stream)
+
+    def _ck(self, rc):
+        self.launches += 1
+        if rc != 0:
+            raise KernelError(f"p2pvg_b200 error {rc}: {self.lib.p2pvg_last_error().decode()}")
+
+    def gemm_workspace(self):
+        if self._gemm_ws is None:
+            self._gemm_ws = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+        return self._gemm_ws
+
+    def bn_workspace(self, G, C):
+        need = self.lib.p2pvg_bn_workspace_bytes(_i(G), _i(C))
+        if self._bn_ws is None or self._bn_ws.numel() < need:
+            self._bn_ws = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=self.device)
+        return self._bn_ws
+
+    def set_gemm_impl(self, impl: str):
+        self._ck(self.lib.p2pvg_set_gemm_impl(_i({"auto": 0, "simt": 1, "tc": 2}[impl])))
+        self.launches -= 1
+
+    def has_tcgen05(self) -> bool:
+        return bool(self.lib.p2pvg_has_tcgen05())
+
+    # -- GEMM ------------------------------------------------------------------------------
+    def gemm(self, A, B, C, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, accumulate=False, bias=None,
+             addend=None, ldd=None):
+        lda = lda if lda is not None else (M if a_mn else K)
+        ldb = ldb if ldb is not None else (N if b_mn else K)
+        ldc = ldc if ldc is not None else N
+        ldd = ldd if ldd is not None else N
+        assert A.dtype == B.dtype
+        ws = self.gemm_workspace() if A.dtype == torch.bfloat16 else None
+        self._ck(self.lib.p2pvg_gemm(_p(A), _i(_dt(A)), _i(int(a_mn)), _i64(lda), _p(B), _i(int(b_mn)), _i64(ldb), _p(C),
+                                     _i(_dt(C)), _i64(ldc), _i(M), _i(N), _i(K), _i(int(accumulate)), _p(bias), _p(addend),
+                                     _i64(ldd), _p(ws), _sz(ws.numel() if ws is not None else 0), self._stream()))
+
+    # -- conv lowering ---------------------------------------------------------------------
+    def im2col(self, x, col, N, H, W, C):
+        self._ck(self.lib.p2pvg_im2col_k4s2p1(_p(x), _p(col), _i(_dt(x)), _i(N), _i(H), _i(W), _i(C), self._stream()))
+
+    def col2im(self, col, y, N, Hi, Wi, C, bias=None, col2=None, grp_src=None, imgs_per_group=0, accumulate=False):
+        self._ck(self.lib.p2pvg_col2im_k4s2p1(_p(col), _p(col2), _p(grp_src), _i(imgs_per_group), _p(y), _i(_dt(col)), _i(N),
+                                              _i(Hi), _i(Wi), _i(C), _p(bias), _i(int(accumulate)), self._stream()))
+
+    def permute4(self, src, dst, dims, strides, accumulate=False):
+        d = (_i * 4)(*dims)
+        s = (_i64 * 4)(*strides)
+        self._ck(self.lib.p2pvg_permute4(_p(src), _i(_dt(src)), _p(dst), _i(_dt(dst)), d, s, _i(int(accumulate)), self._stream()))
+
+    def add_indexed(self, dst, src, dst_idx, F, n):
+        self._ck(self.lib.p2pvg_add_indexed(_p(dst), _p(src), _i(_dt(dst)), _p(dst_idx), _i(F), _i64(n), self._stream()))
+
+    def group_sum(self, inp, out, grp_src, G, F, n):
+        self._ck(self.lib.p2pvg_group_sum(_p(inp), _p(out), _i(_dt(inp)), _p(grp_src), _i(G), _i(F), _i64(n), self._stream()))
+
+    # -- batch norm ------------------------------------------------------------------------
+    def bn_fwd_stats(self, x, G, R, C, gamma, beta, mean, invstd, var_unb, scale, shift, eps=1e-5):
+        ws = self.bn_workspace(G, C)
+        self._ck(self.lib.p2pvg_bn_fwd_stats(_p(x), _i(_dt(x)), _i(G), _i64(R), _i(C), _p(gamma), _p(beta), _f(eps), _p(ws),
+                                             _sz(ws.numel()), _p(mean), _p(invstd), _p(var_unb), _p(scale), _p(shift),
+                                             self._stream()))
+
+    def bn_act(self, x, y, scale, shift, G, R, C, act):
+        self._ck(self.lib.p2pvg_bn_act(_p(x), _p(y), _i(_dt(x)), _p(scale), _p(shift), _i(G), _i64(R), _i(C), _i(act), self._stream()))
+
+    def bn_bwd(self, dy, x, y, mean, invstd, gamma, G, R, C, act, dx, sum_dz, sum_dzx):
+        ws = self.bn_workspace(G, C)
+        self._ck(self.lib.p2pvg_bn_bwd(_p(dy), _p(x), _p(y), _i(_dt(x)), _p(mean), _p(invstd), _p(gamma), _i(G), _i64(R), _i(C),
+                                       _i(act), _p(ws), _sz(ws.numel()), _p(dx), _p(sum_dz), _p(sum_dzx), self._stream()))
+
+    def bn_param_grad(self, sum_dz, sum_dzx, G, C, dgamma, dbeta):
+        self._ck(self.lib.p2pvg_bn_param_grad(_p(sum_dz), _p(sum_dzx), _i(G), _i(C), _p(dgamma), _p(dbeta), self._stream()))
+
+    def bn_ema(self, rmean, rvar, mean, var_unb, order, ncalls, C, momentum=0.1):
+        self._ck(self.lib.p2pvg_bn_ema(_p(rmean), _p(rvar), _p(mean), _p(var_unb), _p(order), _i(ncalls), _i(C), _f(momentum),
+                                       self._stream()))
+
+    # -- recurrent phase -------------------------------------------------------------------
+    def lstm_pointwise_fwd(self, gates, c_prev, c_out, h_out, B, R):
+        self._ck(self.lib.p2pvg_lstm_pointwise_fwd(_p(gates), _p(c_prev), _p(c_out), _p(h_out), _i(B), _i(R), self._stream()))
+
+    def lstm_pointwise_bwd(self, dh, dc_next, gates, c_prev, c, dgates, dc_prev, B, R):
+        self._ck(self.lib.p2pvg_lstm_pointwise_bwd(_p(dh), _p(dc_next), _p(gates), _p(c_prev), _p(c), _p(dgates), _p(dc_prev), _i(B),
+                                                   _i(R), self._stream()))
+
+    def reparam_kl_fwd(self, mu, lv, mu_p, lv_p, eps, eps_p, z, z_p, n, kl_sum):
+        self._ck(self.lib.p2pvg_reparam_kl_fwd(_p(mu), _p(lv), _p(mu_p), _p(lv_p), _p(eps), _p(eps_p), _p(z), _p(z_p), _i(n),
+                                               _p(kl_sum), self._stream()))
+
+    def reparam_kl_bwd(self, mu, lv, mu_p, lv_p, eps, eps_p, dz, dz_p, kl_coef, dmu, dlv, dmu_p, dlv_p, n):
+        self._ck(self.lib.p2pvg_reparam_kl_bwd(_p(mu), _p(lv), _p(mu_p), _p(lv_p), _p(eps), _p(eps_p), _p(dz), _p(dz_p),
+                                               _f(kl_coef), _p(dmu), _p(dlv), _p(dmu_p), _p(dlv_p), _i(n), self._stream()))
+
+    def build_concat(self, dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B):
+        self._ck(self.lib.p2pvg_build_concat(_p(dst), _p(A), _p(ia), _i(ga), _p(Bm), _p(ib), _i(gb), _p(tuc), _p(dt), _i(S), _i(B),
+                                             self._stream()))
+
+    def gather_add_cols(self, dst, src, idx, S, T, B, g, W, col0, init=False):
+        self._ck(self.lib.p2pvg_gather_add_cols(_p(dst), _p(src), _p(idx), _i(S), _i(T), _i(B), _i(g), _i(W), _i(col0),
+                                                _i(int(init)), self._stream()))
+
+    def align(self, H, in_idx, h_pred, P, B, g, coef, loss_partial, d_hpred, dH):
+        self._ck(self.lib.p2pvg_align(_p(H), _p(in_idx), _p(h_pred), _i(P), _i(B), _i(g), _f(coef), _p(loss_partial), _p(d_hpred),
+                                      _p(dH), self._stream()))
+
+    def colsum(self, x, rows, cols, ld, out, accumulate=False):
+        self._ck(self.lib.p2pvg_colsum(_p(x), _i(_dt(x)), _i64(rows), _i(cols), _i64(ld), _p(out), _i(int(accumulate)), self._stream()))
+
+    def act_fwd(self, x, n, act):
+        self._ck(self.lib.p2pvg_act_fwd(_p(x), _i64(n), _i(act), self._stream()))
+
+    def act_bwd(self, dy, y, dx, n, act):
+        self._ck(self.lib.p2pvg_act_bwd(_p(dy), _p(y), _p(dx), _i64(n), _i(act), self._stream()))
+
+    # -- losses / optimiser ----------------------------------------------------------------
+    def mse_chunks(self):
+        return int(self.lib.p2pvg_mse_chunks())
+
+    def sigmoid_mse(self, raw, x, tgt, coef, G, E, pred, d_raw, partial):
+        self._ck(self.lib.p2pvg_sigmoid_mse(_p(raw), _i(_dt(raw)), _p(x), _p(tgt), _p(coef), _i(G), _i64(E), _p(pred), _p(d_raw),
+                                            _p(partial), self._stream()))
+
+    def finalize_losses(self, mse_partial, n_recon, has_cpc, E, kl_sum, batch_size, align_partial, n_align, seq_len, out):
+        self._ck(self.lib.p2pvg_finalize_losses(_p(mse_partial), _i(n_recon), _i(int(has_cpc)), _d(float(E)), _p(kl_sum),
+                                                _f(batch_size), _p(align_partial), _i(n_align), _f(seq_len), _p(out),
+                                                self._stream()))
+
+    def adam(self, p, g, m, v, n, lr, beta1, beta2, eps, step_t):
+        self._ck(self.lib.p2pvg_adam_legacy(_p(p), _p(g), _p(m), _p(v), _i64(n), _d(lr), _d(beta1), _d(beta2), _d(eps),
+                                            _p(step_t), self._stream()))
+
+    def scale(self, x, n, a):
+        self._ck(self.lib.p2pvg_scale(_p(x), _i64(n), _f(a), self._stream()))

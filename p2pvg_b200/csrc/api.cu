@@ -1,0 +1,186 @@
+// extern "C" surface of libp2pvg_b200.so (declared in include/p2pvg_b200.h): argument checking,
+// thread-local error state, GEMM dispatch (tcgen05 vs CUDA-core).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/p2pvg_b200.h"
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void p2pvg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int p2pvg_check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    p2pvg_set_error("%s: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return P2PVG_ERR_CUDA;
+  }
+  return P2PVG_OK;
+}
+
+// ---- implemented in the other translation units ----
+int p2pvg_gemm_simt(const void*, int, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int,
+                    const float*, const void*, long long, cudaStream_t);
+int p2pvg_gemm_tc(const void*, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int, const float*,
+                  const void*, long long, void*, size_t, cudaStream_t);
+int p2pvg_gemm_tc_available();
+int p2pvg_im2col_k4s2p1_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
+int p2pvg_col2im_k4s2p1_impl(const void*, const void*, const int*, int, void*, int, int, int, int, int, const float*, int, cudaStream_t);
+int p2pvg_permute4_impl(const void*, int, void*, int, const int*, const long long*, int, cudaStream_t);
+int p2pvg_add_indexed_impl(void*, const void*, int, const int*, int, long long, cudaStream_t);
+int p2pvg_group_sum_impl(const void*, void*, int, const int*, int, int, long long, cudaStream_t);
+size_t p2pvg_bn_workspace_bytes_impl(int, int);
+int p2pvg_bn_fwd_stats_impl(const void*, int, int, long long, int, const float*, const float*, float, void*, size_t, float*, float*,
+                            float*, float*, float*, cudaStream_t);
+int p2pvg_bn_act_impl(const void*, void*, int, const float*, const float*, int, long long, int, int, cudaStream_t);
+int p2pvg_bn_bwd_impl(const void*, const void*, const void*, int, const float*, const float*, const float*, int, long long, int, int,
+                      void*, size_t, void*, float*, float*, cudaStream_t);
+int p2pvg_bn_param_grad_impl(const float*, const float*, int, int, float*, float*, cudaStream_t);
+int p2pvg_bn_ema_impl(float*, float*, const float*, const float*, const int*, int, int, float, cudaStream_t);
+int p2pvg_lstm_pointwise_fwd_impl(float*, const float*, float*, float*, int, int, cudaStream_t);
+int p2pvg_lstm_pointwise_bwd_impl(const float*, const float*, const float*, const float*, const float*, float*, float*, int, int,
+                                  cudaStream_t);
+int p2pvg_reparam_kl_fwd_impl(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, int,
+                              float*, cudaStream_t);
+int p2pvg_reparam_kl_bwd_impl(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                              const float*, float, float*, float*, float*, float*, int, cudaStream_t);
+int p2pvg_build_concat_impl(float*, const float*, const int*, int, const float*, const int*, int, const float*, const float*, int, int,
+                            cudaStream_t);
+int p2pvg_gather_add_cols_impl(float*, const float*, const int*, int, int, int, int, int, int, int, cudaStream_t);
+int p2pvg_align_impl(const float*, const int*, const float*, int, int, int, float, float*, float*, float*, cudaStream_t);
+int p2pvg_colsum_impl(const void*, int, long long, int, long long, float*, int, cudaStream_t);
+int p2pvg_act_fwd_impl(float*, long long, int, cudaStream_t);
+int p2pvg_act_bwd_impl(const float*, const float*, float*, long long, int, cudaStream_t);
+int p2pvg_mse_chunks_impl();
+int p2pvg_sigmoid_mse_impl(const void*, int, const float*, const int*, const float*, int, long long, void*, void*, float*, cudaStream_t);
+int p2pvg_finalize_losses_impl(const float*, int, int, double, const float*, float, const float*, int, float, float*, cudaStream_t);
+int p2pvg_adam_legacy_impl(float*, const float*, float*, float*, long long, double, double, double, double, const int*, cudaStream_t);
+int p2pvg_scale_impl(float*, long long, float, cudaStream_t);
+
+static int g_gemm_impl = 0;  // 0 auto, 1 simt, 2 tcgen05
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+
+int p2pvg_version(void) { return 100; }
+const char* p2pvg_last_error(void) { return g_err; }
+int p2pvg_has_tcgen05(void) { return p2pvg_gemm_tc_available(); }
+int p2pvg_set_gemm_impl(int impl) {
+  if (impl < 0 || impl > 2) return P2PVG_ERR_BAD_ARG;
+  g_gemm_impl = impl;
+  return P2PVG_OK;
+}
+
+int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int c_dtype,
+               int64_t ldc, int M, int N, int K, int accumulate, const float* bias, const void* addend, int64_t ldd,
+               void* workspace, size_t ws_bytes, void* stream) {
+  P2PVG_REQUIRE(A && B && C, P2PVG_ERR_BAD_ARG, "gemm: null operand");
+  P2PVG_REQUIRE(M >= 0 && N >= 0 && K >= 0, P2PVG_ERR_BAD_ARG, "gemm: negative size");
+  bool want_tc = (in_dtype == P2PVG_BF16) && g_gemm_impl != 1;
+  if (g_gemm_impl == 2 && in_dtype != P2PVG_BF16) {
+    p2pvg_set_error("gemm: tcgen05 path needs bf16 operands");
+    return P2PVG_ERR_UNSUPPORTED;
+  }
+  if (want_tc)
+    return p2pvg_gemm_tc(A, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace, ws_bytes, ST);
+  return p2pvg_gemm_simt(A, in_dtype, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, ST);
+}
+
+int p2pvg_im2col_k4s2p1(const void* x, void* col, int dtype, int N, int H, int W, int C, void* stream) {
+  return p2pvg_im2col_k4s2p1_impl(x, col, dtype, N, H, W, C, ST);
+}
+int p2pvg_col2im_k4s2p1(const void* col, const void* col2, const int* grp_src, int imgs_per_group, void* y, int dtype, int N,
+                        int Hi, int Wi, int C, const float* bias, int accumulate, void* stream) {
+  return p2pvg_col2im_k4s2p1_impl(col, col2, grp_src, imgs_per_group, y, dtype, N, Hi, Wi, C, bias, accumulate, ST);
+}
+int p2pvg_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims, const int64_t* src_strides,
+                   int accumulate, void* stream) {
+  return p2pvg_permute4_impl(src, src_dtype, dst, dst_dtype, dims, (const long long*)src_strides, accumulate, ST);
+}
+int p2pvg_add_indexed(void* dst, const void* src, int dtype, const int* dst_idx, int F, int64_t n, void* stream) {
+  return p2pvg_add_indexed_impl(dst, src, dtype, dst_idx, F, n, ST);
+}
+int p2pvg_group_sum(const void* in, void* out, int dtype, const int* grp_src, int G, int F, int64_t n, void* stream) {
+  return p2pvg_group_sum_impl(in, out, dtype, grp_src, G, F, n, ST);
+}
+size_t p2pvg_bn_workspace_bytes(int G, int C) { return p2pvg_bn_workspace_bytes_impl(G, C); }
+int p2pvg_bn_fwd_stats(const void* x, int dtype, int G, int64_t R, int C, const float* gamma, const float* beta, float eps,
+                       void* ws, size_t ws_bytes, float* mean, float* invstd, float* var_unbiased, float* scale, float* shift,
+                       void* stream) {
+  return p2pvg_bn_fwd_stats_impl(x, dtype, G, R, C, gamma, beta, eps, ws, ws_bytes, mean, invstd, var_unbiased, scale, shift, ST);
+}
+int p2pvg_bn_act(const void* x, void* y, int dtype, const float* scale, const float* shift, int G, int64_t R, int C, int act,
+                 void* stream) {
+  return p2pvg_bn_act_impl(x, y, dtype, scale, shift, G, R, C, act, ST);
+}
+int p2pvg_bn_bwd(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
+                 const float* gamma, int G, int64_t R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
+                 float* sum_dzx, void* stream) {
+  return p2pvg_bn_bwd_impl(dy, x, y, dtype, mean, invstd, gamma, G, R, C, act, ws, ws_bytes, dx, sum_dz, sum_dzx, ST);
+}
+int p2pvg_bn_param_grad(const float* sum_dz, const float* sum_dzx, int G, int C, float* dgamma, float* dbeta, void* stream) {
+  return p2pvg_bn_param_grad_impl(sum_dz, sum_dzx, G, C, dgamma, dbeta, ST);
+}
+int p2pvg_bn_ema(float* rmean, float* rvar, const float* mean, const float* var_unbiased, const int* order, int ncalls, int C,
+                 float momentum, void* stream) {
+  return p2pvg_bn_ema_impl(rmean, rvar, mean, var_unbiased, order, ncalls, C, momentum, ST);
+}
+int p2pvg_lstm_pointwise_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, int B, int R, void* stream) {
+  return p2pvg_lstm_pointwise_fwd_impl(gates, c_prev, c_out, h_out, B, R, ST);
+}
+int p2pvg_lstm_pointwise_bwd(const float* dh, const float* dc_next, const float* gates, const float* c_prev, const float* c,
+                             float* dgates, float* dc_prev, int B, int R, void* stream) {
+  return p2pvg_lstm_pointwise_bwd_impl(dh, dc_next, gates, c_prev, c, dgates, dc_prev, B, R, ST);
+}
+int p2pvg_reparam_kl_fwd(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,
+                         const float* eps_p, float* z, float* z_p, int n, float* kl_sum, void* stream) {
+  return p2pvg_reparam_kl_fwd_impl(mu, lv, mu_p, lv_p, eps, eps_p, z, z_p, n, kl_sum, ST);
+}
+int p2pvg_reparam_kl_bwd(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,
+                         const float* eps_p, const float* dz, const float* dz_p, float kl_coef, float* dmu, float* dlv,
+                         float* dmu_p, float* dlv_p, int n, void* stream) {
+  return p2pvg_reparam_kl_bwd_impl(mu, lv, mu_p, lv_p, eps, eps_p, dz, dz_p, kl_coef, dmu, dlv, dmu_p, dlv_p, n, ST);
+}
+int p2pvg_build_concat(float* dst, const float* A, const int* ia, int ga, const float* Bm, const int* ib, int gb,
+                       const float* tuc, const float* dt, int S, int B, void* stream) {
+  return p2pvg_build_concat_impl(dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B, ST);
+}
+int p2pvg_gather_add_cols(float* dst, const float* src, const int* idx, int S, int T, int B, int g, int W, int col0, int init,
+                          void* stream) {
+  return p2pvg_gather_add_cols_impl(dst, src, idx, S, T, B, g, W, col0, init, ST);
+}
+int p2pvg_align(const float* H, const int* in_idx, const float* h_pred, int P, int B, int g, float coef, float* loss_partial,
+                float* d_hpred, float* dH, void* stream) {
+  return p2pvg_align_impl(H, in_idx, h_pred, P, B, g, coef, loss_partial, d_hpred, dH, ST);
+}
+int p2pvg_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* out, int accumulate, void* stream) {
+  return p2pvg_colsum_impl(x, dtype, rows, cols, ld, out, accumulate, ST);
+}
+int p2pvg_act_fwd(float* x, int64_t n, int act, void* stream) { return p2pvg_act_fwd_impl(x, n, act, ST); }
+int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream) {
+  return p2pvg_act_bwd_impl(dy, y, dx, n, act, ST);
+}
+int p2pvg_mse_chunks(void) { return p2pvg_mse_chunks_impl(); }
+int p2pvg_sigmoid_mse(const void* raw, int dtype, const float* x, const int* tgt, const float* coef, int G, int64_t E,
+                      void* pred, void* d_raw, float* partial, void* stream) {
+  return p2pvg_sigmoid_mse_impl(raw, dtype, x, tgt, coef, G, E, pred, d_raw, partial, ST);
+}
+int p2pvg_finalize_losses(const float* mse_partial, int n_recon, int has_cpc, double E, const float* kl_sum, float batch_size,
+                          const float* align_partial, int n_align, float seq_len, float* out, void* stream) {
+  return p2pvg_finalize_losses_impl(mse_partial, n_recon, has_cpc, E, kl_sum, batch_size, align_partial, n_align, seq_len, out, ST);
+}
+int p2pvg_adam_legacy(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                      double eps, const int* step_ptr, void* stream) {
+  return p2pvg_adam_legacy_impl(p, g, m, v, n, lr, beta1, beta2, eps, step_ptr, ST);
+}
+int p2pvg_scale(float* x, int64_t n, float a, void* stream) { return p2pvg_scale_impl(x, n, a, ST); }
+
+}  // extern "C"

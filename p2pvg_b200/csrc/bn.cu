@@ -1,0 +1,291 @@
+// Training-mode BatchNorm over NHWC activations with statistics grouped per original module call
+// (group g = one encoder/decoder call of the reference).  x is [G, R, C] with R rows
+// (= B*H*W) per group.  Reductions are deterministic two-stage (per-chunk partials in fp64, then a
+// finalize kernel); all kernels are streaming / HBM-bound.
+#include "common.cuh"
+
+#define BN_MAXCHUNK 64
+
+namespace {
+
+__device__ __forceinline__ float act_grad(float y, int act) {
+  if (act == P2PVG_ACT_LRELU) return y > 0.f ? 1.f : 0.2f;
+  if (act == P2PVG_ACT_TANH) return 1.f - y * y;
+  return 1.f;
+}
+
+// MODE 0: (sum x, sum x^2).  MODE 1: (sum dz, sum dz*xhat), dz = dy*act'(y), xhat=(x-mean)*invstd
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
+                                                        const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                                                        long long R, int C, int rows_per_chunk, double2* __restrict__ partial) {
+  const int CV = C >> 2;
+  const int lanes = 256 / CV;
+  const int cv = threadIdx.x % CV, lane = threadIdx.x / CV;
+  const int g = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const long long r0 = (long long)chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > R) r1 = R;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  float mu[4] = {0, 0, 0, 0}, is[4] = {0, 0, 0, 0};
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      mu[j] = mean[(long long)g * C + cv * 4 + j];
+      is[j] = invstd[(long long)g * C + cv * 4 + j];
+    }
+  }
+  if (lane < lanes) {
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+      const long long off = ((long long)g * R + r) * C + cv * 4;
+      f4 xv = ld_f4<T>(x + off);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          s0[j] += xv.v[j];
+          s1[j] = fmaf(xv.v[j], xv.v[j], s1[j]);
+        }
+      } else {
+        f4 dv = ld_f4<T>(dy + off);
+        f4 yv = ld_f4<T>(y + off);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float dz = dv.v[j] * act_grad(yv.v[j], act);
+          s0[j] += dz;
+          s1[j] = fmaf(dz, (xv.v[j] - mu[j]) * is[j], s1[j]);
+        }
+      }
+    }
+  }
+  __shared__ double sh0[256 * 4];
+  __shared__ double sh1[256 * 4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    sh0[threadIdx.x * 4 + j] = (lane < lanes) ? (double)s0[j] : 0.0;
+    sh1[threadIdx.x * 4 + j] = (lane < lanes) ? (double)s1[j] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    // channel c = threadIdx.x: vector cvv = c/4, component j = c%4; sum over lanes
+    const int cvv = threadIdx.x >> 2, j = threadIdx.x & 3;
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < lanes; l++) {
+      a += sh0[(l * CV + cvv) * 4 + j];
+      b += sh1[(l * CV + cvv) * 4 + j];
+    }
+    partial[((long long)g * nchunk + chunk) * C + threadIdx.x] = make_double2(a, b);
+  }
+  // C can exceed 256 threads? No: C/4 <= 256 but C may be up to 1024 -> loop
+  for (int c = threadIdx.x + 256; c < C; c += 256) {
+    const int cvv = c >> 2, j = c & 3;
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < lanes; l++) {
+      a += sh0[(l * CV + cvv) * 4 + j];
+      b += sh1[(l * CV + cvv) * 4 + j];
+    }
+    partial[((long long)g * nchunk + chunk) * C + c] = make_double2(a, b);
+  }
+}
+
+__global__ void bn_fwd_finalize_kernel(const double2* __restrict__ partial, int nchunk, int G, int C, long long R,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                       float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ var_unbiased,
+                                       float* __restrict__ scale, float* __restrict__ shift) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * C) return;
+  int g = idx / C, c = idx % C;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nchunk; k++) {
+    double2 p = partial[((long long)g * nchunk + k) * C + c];
+    a += p.x;
+    b += p.y;
+  }
+  double m = a / (double)R;
+  double var = b / (double)R - m * m;
+  if (var < 0.0) var = 0.0;
+  double is = 1.0 / sqrt(var + (double)eps);
+  mean[idx] = (float)m;
+  invstd[idx] = (float)is;
+  var_unbiased[idx] = (float)(R > 1 ? var * (double)R / (double)(R - 1) : var);
+  float sc = gamma[c] * (float)is;
+  scale[idx] = sc;
+  shift[idx] = beta[c] - (float)m * sc;
+}
+
+__global__ void bn_bwd_finalize_kernel(const double2* __restrict__ partial, int nchunk, int G, int C,
+                                       float* __restrict__ sum_dz, float* __restrict__ sum_dzx) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * C) return;
+  int g = idx / C, c = idx % C;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nchunk; k++) {
+    double2 p = partial[((long long)g * nchunk + k) * C + c];
+    a += p.x;
+    b += p.y;
+  }
+  sum_dz[idx] = (float)a;
+  sum_dzx[idx] = (float)b;
+}
+
+template <typename T>
+__global__ void bn_act_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
+                              const float* __restrict__ shift, long long R, int C, long long total4, int act) {
+  const int CV = C >> 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    long long row = idx / CV;
+    int g = (int)(row / R);
+    f4 v = ld_f4<T>(x + idx * 4);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + (long long)g * C + cv * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + (long long)g * C + cv * 4);
+    float s[4] = {sc.x, sc.y, sc.z, sc.w}, h[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float z = fmaf(v.v[j], s[j], h[j]);
+      if (act == P2PVG_ACT_LRELU) z = z > 0.f ? z : 0.2f * z;
+      else if (act == P2PVG_ACT_TANH) z = tanhf(z);
+      v.v[j] = z;
+    }
+    st_f4<T>(y + idx * 4, v);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sum_dz,
+                                    const float* __restrict__ sum_dzx, long long R, int C, long long total4, int act,
+                                    T* __restrict__ dx) {
+  const int CV = C >> 2;
+  const float invR = 1.f / (float)R;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    long long row = idx / CV;
+    int g = (int)(row / R);
+    f4 dv = ld_f4<T>(dy + idx * 4);
+    f4 xv = ld_f4<T>(x + idx * 4);
+    f4 yv = ld_f4<T>(y + idx * 4);
+    f4 o;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const long long gc = (long long)g * C + cv * 4 + j;
+      float is = invstd[gc];
+      float xhat = (xv.v[j] - mean[gc]) * is;
+      float dz = dv.v[j] * act_grad(yv.v[j], act);
+      o.v[j] = gamma[cv * 4 + j] * is * (dz - sum_dz[gc] * invR - xhat * sum_dzx[gc] * invR);
+    }
+    st_f4<T>(dx + idx * 4, o);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx, int G, int C,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int g = 0; g < G; g++) {
+    a += sum_dzx[(long long)g * C + c];
+    b += sum_dz[(long long)g * C + c];
+  }
+  dgamma[c] = a;
+  dbeta[c] = b;
+}
+
+__global__ void bn_ema_kernel(float* __restrict__ rmean, float* __restrict__ rvar, const float* __restrict__ mean,
+                              const float* __restrict__ var_unbiased, const int* __restrict__ order, int ncalls, int C,
+                              float momentum) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m = rmean[c], v = rvar[c];
+  for (int k = 0; k < ncalls; k++) {
+    int g = order[k];
+    m = (1.f - momentum) * m + momentum * mean[(long long)g * C + c];
+    v = (1.f - momentum) * v + momentum * var_unbiased[(long long)g * C + c];
+  }
+  rmean[c] = m;
+  rvar[c] = v;
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+struct Chunking {
+  int nchunk, rows_per_chunk;
+};
+inline Chunking choose_chunks(long long R, int C) {
+  int lanes = 256 / (C / 4);
+  if (lanes < 1) lanes = 1;
+  long long want = (R + (long long)lanes * 16 - 1) / ((long long)lanes * 16);  // >=16 rows per thread
+  int nchunk = (int)(want < 1 ? 1 : (want > BN_MAXCHUNK ? BN_MAXCHUNK : want));
+  int rpc = (int)((R + nchunk - 1) / nchunk);
+  nchunk = (int)((R + rpc - 1) / rpc);
+  return Chunking{nchunk, rpc};
+}
+
+inline int check_bn_shape(int C, const char* what) {
+  int CV = C / 4;
+  if (C % 4 != 0 || CV > 256 || (256 % CV) != 0) {
+    p2pvg_set_error("%s: unsupported channel count %d (need C%%4==0, C/4 a divisor of 256)", what, C);
+    return P2PVG_ERR_UNSUPPORTED;
+  }
+  return P2PVG_OK;
+}
+
+}  // namespace
+
+size_t p2pvg_bn_workspace_bytes_impl(int G, int C) { return (size_t)G * BN_MAXCHUNK * C * sizeof(double2); }
+
+int p2pvg_bn_fwd_stats_impl(const void* x, int dtype, int G, long long R, int C, const float* gamma, const float* beta, float eps,
+                            void* ws, size_t ws_bytes, float* mean, float* invstd, float* var_unbiased, float* scale,
+                            float* shift, cudaStream_t st) {
+  if (int e = check_bn_shape(C, "bn_fwd_stats")) return e;
+  P2PVG_REQUIRE(ws_bytes >= p2pvg_bn_workspace_bytes_impl(G, C), P2PVG_ERR_WORKSPACE, "bn_fwd_stats: workspace too small");
+  if (G == 0) return P2PVG_OK;
+  Chunking ch = choose_chunks(R, C);
+  dim3 grid(ch.nchunk, G);
+  DISPATCH_DTYPE(dtype, T, (bn_reduce_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, 0, R, C,
+                                                                         ch.rows_per_chunk, (double2*)ws)));
+  bn_fwd_finalize_kernel<<<cdiv((long long)G * C, 256), 256, 0, st>>>((const double2*)ws, ch.nchunk, G, C, R, gamma, beta, eps, mean,
+                                                                      invstd, var_unbiased, scale, shift);
+  return p2pvg_check_launch("bn_fwd_stats");
+}
+
+int p2pvg_bn_act_impl(const void* x, void* y, int dtype, const float* scale, const float* shift, int G, long long R, int C, int act,
+                      cudaStream_t st) {
+  P2PVG_REQUIRE(C % 4 == 0, P2PVG_ERR_UNSUPPORTED, "bn_act: C %% 4 != 0");
+  long long total4 = (long long)G * R * (C / 4);
+  if (total4 == 0) return P2PVG_OK;
+  DISPATCH_DTYPE(dtype, T, (bn_act_kernel<T><<<grid_for(total4, 256), 256, 0, st>>>((const T*)x, (T*)y, scale, shift, R, C, total4, act)));
+  return p2pvg_check_launch("bn_act");
+}
+
+int p2pvg_bn_bwd_impl(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
+                      const float* gamma, int G, long long R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
+                      float* sum_dzx, cudaStream_t st) {
+  if (int e = check_bn_shape(C, "bn_bwd")) return e;
+  P2PVG_REQUIRE(ws_bytes >= p2pvg_bn_workspace_bytes_impl(G, C), P2PVG_ERR_WORKSPACE, "bn_bwd: workspace too small");
+  if (G == 0) return P2PVG_OK;
+  Chunking ch = choose_chunks(R, C);
+  dim3 grid(ch.nchunk, G);
+  DISPATCH_DTYPE(dtype, T, (bn_reduce_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, act, R, C,
+                                                                         ch.rows_per_chunk, (double2*)ws)));
+  bn_bwd_finalize_kernel<<<cdiv((long long)G * C, 256), 256, 0, st>>>((const double2*)ws, ch.nchunk, G, C, sum_dz, sum_dzx);
+  long long total4 = (long long)G * R * (C / 4);
+  DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<grid_for(total4, 256), 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, mean, invstd,
+                                                                                          gamma, sum_dz, sum_dzx, R, C, total4, act, (T*)dx)));
+  return p2pvg_check_launch("bn_bwd");
+}
+
+int p2pvg_bn_param_grad_impl(const float* sum_dz, const float* sum_dzx, int G, int C, float* dgamma, float* dbeta, cudaStream_t st) {
+  bn_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(sum_dz, sum_dzx, G, C, dgamma, dbeta);
+  return p2pvg_check_launch("bn_param_grad");
+}
+
+int p2pvg_bn_ema_impl(float* rmean, float* rvar, const float* mean, const float* var_unbiased, const int* order, int ncalls, int C,
+                      float momentum, cudaStream_t st) {
+  bn_ema_kernel<<<cdiv(C, 128), 128, 0, st>>>(rmean, rvar, mean, var_unbiased, order, ncalls, C, momentum);
+  return p2pvg_check_launch("bn_ema");
+}

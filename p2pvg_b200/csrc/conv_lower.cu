@@ -1,0 +1,227 @@
+// Lowering kernels that turn the dcgan 4x4/stride-2/pad-1 (transposed) convolutions into GEMMs on
+// NHWC activations, plus the small layout utilities (permute / cast / indexed add / segment sum).
+// All of them are HBM-bound streaming kernels: one thread per 4 channels, fully coalesced on the
+// channel axis.
+#include "common.cuh"
+
+namespace {
+
+// ---- im2col: x [N,H,W,C] -> col [N*(H/2)*(W/2), 16*C], K order (kh, kw, c) ----------------------
+template <typename T, int V>
+__global__ void im2col_k4s2p1_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, CV = C / V;
+  const long long total = (long long)N * Ho * Wo * 16 * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    int tap = (int)(r & 15);
+    long long row = r >> 4;
+    int ox = (int)(row % Wo);
+    long long t = row / Wo;
+    int oy = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
+    T* dst = col + (row * 16 + tap) * C + cv * V;
+    bool ok = (iy >= 0 && iy < H && ix >= 0 && ix < W);
+    const T* src = x + (((long long)n * H + iy) * W + ix) * C + cv * V;
+    if (V == 4) {
+      f4 v = {{0.f, 0.f, 0.f, 0.f}};
+      if (ok) v = ld_f4<T>(src);
+      st_f4<T>(dst, v);
+    } else {
+      st_f<T>(dst, ok ? ld_f<T>(src) : 0.f);
+    }
+  }
+}
+
+// ---- col2im (gather form): y [N,2Hi,2Wi,C] <- col [N*Hi*Wi, 16*C] (+ col2 of a shared source) ----
+template <typename T, int V>
+__global__ void col2im_k4s2p1_kernel(const T* __restrict__ col, const T* __restrict__ col2, const int* __restrict__ grp_src,
+                                     int imgs_per_group, T* __restrict__ y, int N, int Hi, int Wi, int C,
+                                     const float* __restrict__ bias, int accumulate) {
+  const int Ho = Hi * 2, Wo = Wi * 2, CV = C / V;
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    long long p = idx / CV;
+    int ox = (int)(p % Wo);
+    long long t = p / Wo;
+    int oy = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    int n2 = 0;
+    if (col2) n2 = grp_src[n / imgs_per_group] * imgs_per_group + (n % imgs_per_group);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) acc[j] = bias ? bias[cv * V + j] : 0.f;
+    const int kh0 = (oy + 1) & 1, kw0 = (ox + 1) & 1;
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      int kh = kh0 + 2 * a;
+      int iy = (oy + 1 - kh) >> 1;  // exact: oy+1-kh is even
+      if (oy + 1 - kh < 0 || iy >= Hi) continue;
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        int kw = kw0 + 2 * b;
+        int ix = (ox + 1 - kw) >> 1;
+        if (ox + 1 - kw < 0 || ix >= Wi) continue;
+        long long off = ((((long long)n * Hi + iy) * Wi + ix) * 16 + kh * 4 + kw) * C + cv * V;
+        if (V == 4) {
+          f4 v = ld_f4<T>(col + off);
+#pragma unroll
+          for (int j = 0; j < V; j++) acc[j] += v.v[j];
+        } else {
+          acc[0] += ld_f<T>(col + off);
+        }
+        if (col2) {
+          long long off2 = ((((long long)n2 * Hi + iy) * Wi + ix) * 16 + kh * 4 + kw) * C + cv * V;
+          if (V == 4) {
+            f4 v = ld_f4<T>(col2 + off2);
+#pragma unroll
+            for (int j = 0; j < V; j++) acc[j] += v.v[j];
+          } else {
+            acc[0] += ld_f<T>(col2 + off2);
+          }
+        }
+      }
+    }
+    T* dst = y + p * C + cv * V;
+    if (V == 4) {
+      f4 o;
+      if (accumulate) {
+        o = ld_f4<T>(dst);
+#pragma unroll
+        for (int j = 0; j < V; j++) o.v[j] += acc[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; j++) o.v[j] = acc[j];
+      }
+      st_f4<T>(dst, o);
+    } else {
+      st_f<T>(dst, accumulate ? ld_f<T>(dst) + acc[0] : acc[0]);
+    }
+  }
+}
+
+// ---- generic 4-D permute / cast: dst (contiguous, dims d[0..3]) <- src with per-dst-dim strides ---
+struct Perm4 {
+  int d[4];
+  long long s[4];
+};
+template <typename TS, typename TD>
+__global__ void permute4_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Perm4 p, int accumulate) {
+  const long long total = (long long)p.d[0] * p.d[1] * p.d[2] * p.d[3];
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    int i3 = (int)(r % p.d[3]); r /= p.d[3];
+    int i2 = (int)(r % p.d[2]); r /= p.d[2];
+    int i1 = (int)(r % p.d[1]); r /= p.d[1];
+    int i0 = (int)r;
+    float v = ld_f<TS>(src + i0 * p.s[0] + i1 * p.s[1] + i2 * p.s[2] + i3 * p.s[3]);
+    if (accumulate) v += ld_f<TD>(dst + idx);
+    st_f<TD>(dst + idx, v);
+  }
+}
+
+// ---- dst[dst_idx[f]] += src[f] over F groups of n elements -------------------------------------
+template <typename T>
+__global__ void add_indexed_kernel(T* __restrict__ dst, const T* __restrict__ src, const int* __restrict__ dst_idx, int F, long long n) {
+  const long long total = (long long)F * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(idx / n);
+    long long j = idx - (long long)f * n;
+    T* d = dst + (long long)dst_idx[f] * n + j;
+    st_f<T>(d, ld_f<T>(d) + ld_f<T>(src + idx));
+  }
+}
+
+// ---- out[f] = sum over groups g with src[g]==f of in[g]  (n elements per group, n % 4 == 0) -----
+template <typename T>
+__global__ void group_sum_kernel(const T* __restrict__ in, T* __restrict__ out, const int* __restrict__ grp_src, int G, int F, long long n4) {
+  const long long total = (long long)F * n4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(idx / n4);
+    long long j = idx - (long long)f * n4;
+    f4 acc = {{0.f, 0.f, 0.f, 0.f}};
+    for (int g = 0; g < G; g++) {
+      if (grp_src[g] != f) continue;
+      f4 v = ld_f4<T>(in + ((long long)g * n4 + j) * 4);
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc.v[q] += v.v[q];
+    }
+    st_f4<T>(out + idx * 4, acc);
+  }
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int p2pvg_im2col_k4s2p1_impl(const void* x, void* col, int dtype, int N, int H, int W, int C, cudaStream_t st) {
+  P2PVG_REQUIRE((H % 2 == 0) && (W % 2 == 0), P2PVG_ERR_BAD_ARG, "im2col: odd spatial size %dx%d", H, W);
+  if (N == 0) return P2PVG_OK;
+  if (C % 4 == 0) {
+    long long total = (long long)N * (H / 2) * (W / 2) * 16 * (C / 4);
+    DISPATCH_DTYPE(dtype, T, (im2col_k4s2p1_kernel<T, 4><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
+  } else {
+    long long total = (long long)N * (H / 2) * (W / 2) * 16 * C;
+    DISPATCH_DTYPE(dtype, T, (im2col_k4s2p1_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
+  }
+  return p2pvg_check_launch("im2col_k4s2p1");
+}
+
+int p2pvg_col2im_k4s2p1_impl(const void* col, const void* col2, const int* grp_src, int imgs_per_group, void* y, int dtype,
+                             int N, int Hi, int Wi, int C, const float* bias, int accumulate, cudaStream_t st) {
+  if (N == 0) return P2PVG_OK;
+  P2PVG_REQUIRE(col2 == nullptr || (grp_src != nullptr && imgs_per_group > 0), P2PVG_ERR_BAD_ARG, "col2im: col2 needs grp_src");
+  if (C % 4 == 0) {
+    long long total = (long long)N * Hi * 2 * Wi * 2 * (C / 4);
+    DISPATCH_DTYPE(dtype, T, (col2im_k4s2p1_kernel<T, 4><<<grid_for(total, 256), 256, 0, st>>>(
+                                 (const T*)col, (const T*)col2, grp_src, imgs_per_group, (T*)y, N, Hi, Wi, C, bias, accumulate)));
+  } else {
+    long long total = (long long)N * Hi * 2 * Wi * 2 * C;
+    DISPATCH_DTYPE(dtype, T, (col2im_k4s2p1_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>(
+                                 (const T*)col, (const T*)col2, grp_src, imgs_per_group, (T*)y, N, Hi, Wi, C, bias, accumulate)));
+  }
+  return p2pvg_check_launch("col2im_k4s2p1");
+}
+
+int p2pvg_permute4_impl(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims, const long long* src_strides,
+                        int accumulate, cudaStream_t st) {
+  Perm4 p;
+  long long total = 1;
+  for (int i = 0; i < 4; i++) {
+    p.d[i] = dims[i];
+    p.s[i] = src_strides[i];
+    total *= dims[i];
+  }
+  if (total == 0) return P2PVG_OK;
+  int g = grid_for(total, 256);
+#define L(TS, TD) permute4_kernel<TS, TD><<<g, 256, 0, st>>>((const TS*)src, (TD*)dst, p, accumulate)
+  if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_F32) L(float, float);
+  else if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_BF16) L(float, bf16);
+  else if (src_dtype == P2PVG_BF16 && dst_dtype == P2PVG_F32) L(bf16, float);
+  else if (src_dtype == P2PVG_BF16 && dst_dtype == P2PVG_BF16) L(bf16, bf16);
+  else {
+    p2pvg_set_error("permute4: bad dtypes");
+    return P2PVG_ERR_BAD_ARG;
+  }
+#undef L
+  return p2pvg_check_launch("permute4");
+}
+
+int p2pvg_add_indexed_impl(void* dst, const void* src, int dtype, const int* dst_idx, int F, long long n, cudaStream_t st) {
+  if (F == 0 || n == 0) return P2PVG_OK;
+  DISPATCH_DTYPE(dtype, T, (add_indexed_kernel<T><<<grid_for((long long)F * n, 256), 256, 0, st>>>((T*)dst, (const T*)src, dst_idx, F, n)));
+  return p2pvg_check_launch("add_indexed");
+}
+
+int p2pvg_group_sum_impl(const void* in, void* out, int dtype, const int* grp_src, int G, int F, long long n, cudaStream_t st) {
+  P2PVG_REQUIRE(n % 4 == 0, P2PVG_ERR_BAD_ARG, "group_sum: n must be a multiple of 4");
+  if (F == 0 || n == 0) return P2PVG_OK;
+  DISPATCH_DTYPE(dtype, T, (group_sum_kernel<T><<<grid_for((long long)F * (n / 4), 256), 256, 0, st>>>((const T*)in, (T*)out, grp_src, G, F, n / 4)));
+  return p2pvg_check_launch("group_sum");
+}

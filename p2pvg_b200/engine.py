@@ -1,0 +1,728 @@
+"""Host-side schedule of one p2pvg training step on the sm_100a kernels.
+
+Restructures ``P2PModel.forward`` (reference models/p2p_model.py:185-271) into time-batched phases
+ without changing its results:
+
+  Phase E  every frame is encoded once, BatchNorm statistics grouped per frame (= per reference call);
+  Phase R  posterior / prior / frame-predictor LSTMs: input-side GEMMs batched over time, the recurrent
+           part scanned step by step; reparameterisation, KL and the alignment loss fused;
+  Phase D  all S recon decodes + the CPC decode in one batch, BatchNorm grouped per call, the skip half of
+           every ``torch.cat([d, skip])`` ConvTranspose computed once per distinct skip frame;
+  backward D -> R -> E, Adam on (predictor, posterior, encoder, decoder), then the CPC chain through the
+  *updated* decoder / predictor weights into the prior (the reference's two-phase update on its pinned
+  PyTorch 1.0, "Mode A" of SURVEY.md §8c), Adam on the prior.
+
+The engine only sequences kernels of a backend object (p2pvg_b200._lib.CudaKernels); all arithmetic on
+device data happens inside those kernels.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+BN_MOMENTUM = 0.1
+
+
+def skip_schedule(seq_len, probs, skip_prob, n_past):
+    """Executed timesteps and their (time_until_cp, delta_time) counters — integer / exact-rational logic
+    of models/p2p_model.py:209-229, computed on the host in Python doubles exactly like the reference."""
+    cp_ix = seq_len - 1
+    prev_i, skip_count, out = 0, 0, []
+    max_skip = seq_len * skip_prob
+    for i in range(1, seq_len):
+        if probs[i - 1] <= skip_prob and i >= n_past and skip_count < max_skip and i != 1 and i != cp_ix:
+            skip_count += 1
+            continue
+        out.append((i, (cp_ix - i + 1) / cp_ix, (i - prev_i) / cp_ix))
+        prev_i = i
+    return out
+
+
+class StepPlan:
+    """Index tables of one step (which frame feeds which call), built on the host."""
+
+    def __init__(self, T, probs, opt):
+        sched = skip_schedule(T, probs, opt["skip_prob"], opt["n_past"])
+        self.T, self.S = T, len(sched)
+        S = self.S
+        self.in_frame = [i - 1 for i, _, _ in sched]
+        self.tgt_frame = [i for i, _, _ in sched]
+        self.tuc = [t for _, t, _ in sched]
+        self.dt = [d for _, _, d in sched]
+        src, cur = [], None
+        for i, _, _ in sched:  # models/p2p_model.py:235-238
+            if opt["last_frame_skip"] or i <= opt["n_past"]:
+                cur = i - 1
+            if cur is None:
+                raise ValueError("n_past must be >= 1 (the reference has no skip tensor otherwise)")
+            src.append(cur)
+        self.skip_src = src + [src[-1]]  # the CPC decode reuses the last skip
+        self.nskip = max(self.skip_src) + 1
+        self.has_cpc = S > 0 and sched[-1][0] == T - 1
+        # encoder call order of the reference: x_cp, then (x[i-1], x[i]) per executed step
+        self.enc_order = [T - 1] + [f for s in range(S) for f in (self.in_frame[s], self.tgt_frame[s])]
+        ints = OrderedDict(
+            in_idx=self.in_frame + [self.in_frame[-1]],
+            tgt_idx=self.tgt_frame + [T - 1],          # last entry: CPC target x_cp
+            glob_idx=[T - 1] * (S + 1),
+            z_idx=list(range(S + 1)),
+            skip_src=self.skip_src,
+            enc_order=self.enc_order,
+            dec_order=list(range(S + 1)),
+            skip_dst=list(range(self.nskip)),
+        )
+        self.int_layout, off, flat = {}, 0, []
+        for k, v in ints.items():
+            self.int_layout[k] = (off, len(v))
+            flat += v
+            off += len(v)
+        self.int_host = torch.tensor(flat, dtype=torch.int32)
+        self.f_host = torch.tensor([self.tuc + [self.tuc[-1]], self.dt + [self.dt[-1]]], dtype=torch.float64).float()
+        self.key = (T, S, self.nskip, self.has_cpc)
+
+
+class ParamArena:
+    """Flat fp32 storage of one module's parameters (+ grads + Adam moments) with named views, so the
+    optimiser is one kernel and the data-parallel gradient exchange one all-reduce per module."""
+
+    def __init__(self, named_tensors, device):
+        self.names, self.shapes, self.offsets = [], {}, {}
+        off = 0
+        for k, v in named_tensors.items():
+            self.names.append(k)
+            self.shapes[k] = tuple(v.shape)
+            self.offsets[k] = off
+            off += (v.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        self.step_t = torch.zeros(1, dtype=torch.int32, device=device)
+        self.p, self.g = {}, {}
+        for k, v in named_tensors.items():
+            o, n = self.offsets[k], v.numel()
+            self.p[k] = self.flat[o:o + n].view(self.shapes[k])
+            self.g[k] = self.grad[o:o + n].view(self.shapes[k])
+            self.p[k].copy_(v.detach().to(device=device, dtype=torch.float32))
+
+    def moment_views(self, k):
+        o, n = self.offsets[k], int(np.prod(self.shapes[k])) if self.shapes[k] else 1
+        return self.m[o:o + n].view(self.shapes[k]), self.v[o:o + n].view(self.shapes[k])
+
+
+def is_param_key(key):
+    return not (key.endswith("running_mean") or key.endswith("running_var") or key.endswith("num_batches_tracked"))
+
+
+class TrainEngine:
+    def __init__(self, state, cfg, opt, kernels, act_dtype=torch.float32, mode="A"):
+        """state: module -> {state_dict key: tensor} (reference key names)."""
+        self.K = kernels
+        self.dev = kernels.device
+        self.cfg, self.opt = dict(cfg), dict(opt)
+        self.adt = act_dtype
+        self.mode = mode
+        self.g, self.z, self.R = cfg["g_dim"], cfg["z_dim"], cfg["rnn_size"]
+        self.nc, self.W0 = cfg["channels"], cfg["image_width"]
+        self.chans = [64, 128, 256, 512] if self.W0 == 64 else [64, 128, 256, 512, 512]
+        if self.W0 not in (64, 128):
+            raise ValueError("dcgan backbones exist for 64 and 128 pixel frames")
+        self.n = len(self.chans)
+        self.arena, self.buffers = {}, {}
+        for m in ("frame_predictor", "posterior", "prior", "encoder", "decoder"):
+            params = OrderedDict((k, v) for k, v in state[m].items() if is_param_key(k))
+            self.arena[m] = ParamArena(params, self.dev)
+            self.buffers[m] = {k: v.detach().clone().to(self.dev) for k, v in state[m].items() if not is_param_key(k)}
+        self._bufs = {}
+        self._packed = {}
+        self.last_plan = None
+
+    # ------------------------------------------------------------------ memory
+    def buf(self, name, numel, dtype=None):
+        dtype = dtype or self.adt
+        t = self._bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.zeros(int(numel), dtype=dtype, device=self.dev)
+            self._bufs[name] = t
+        return t
+
+    def fbuf(self, name, numel):
+        return self.buf(name, numel, torch.float32)
+
+    # ------------------------------------------------------------------ weights
+    def enc_names(self, l):
+        if l < self.n:
+            return f"c{l + 1}.main.0", f"c{l + 1}.main.1"
+        return f"c{self.n + 1}.0", f"c{self.n + 1}.1"
+
+    def dec_names(self, k):
+        """k = -1: upc1;  k in [0, n-1]: the stride-2 stages (the last one has no BatchNorm)."""
+        if k < 0:
+            return "upc1.0", "upc1.1"
+        if k < self.n - 1:
+            return f"upc{k + 2}.main.0", f"upc{k + 2}.main.1"
+        return f"upc{self.n + 1}.0", None
+
+    def pack_weights(self, which=("encoder", "decoder")):
+        """fp32 master weights -> GEMM-layout copies in the activation dtype.
+        Conv   W[Cout,Cin,4,4]  -> Wp[Cout,(kh,kw,ci)];   ConvT  W[Cin,Cout,4,4] -> Wp[Cin,(kh,kw,co)]."""
+        K = self.K
+        if "encoder" in which:
+            P = self.arena["encoder"].p
+            for l in range(self.n + 1):
+                w = P[self.enc_names(l)[0] + ".weight"]
+                co, ci = w.shape[0], w.shape[1]
+                wp = self.buf(f"wp_enc{l}", co * 16 * ci)
+                K.permute4(w, wp, (co, 4, 4, ci), (ci * 16, 4, 1, 16))
+                self._packed[f"enc{l}"] = wp
+        if "decoder" in which:
+            P = self.arena["decoder"].p
+            for k in range(-1, self.n):
+                cn = self.dec_names(k)[0]
+                w = P[cn + ".weight"]
+                ci, co = w.shape[0], w.shape[1]
+                wp = self.buf(f"wp_dec{k}", ci * 16 * co)
+                K.permute4(w, wp, (ci, 4, 4, co), (co * 16, 4, 1, 16))
+                self._packed[f"dec{k}"] = wp
+                if k == -1:  # bias of the 1x1 -> 4x4 ConvTranspose, repeated over the 16 taps
+                    b16 = self.fbuf("bias16_upc1", 16 * co)
+                    K.permute4(P[cn + ".bias"], b16, (16, co, 1, 1), (0, 1, 0, 0))
+                    self._packed["dec-1.bias16"] = b16
+
+    # ------------------------------------------------------------------ plan upload
+    def upload_plan(self, plan):
+        ints = self.buf("plan_int", 16 * 1024, torch.int32)
+        fl = self.fbuf("plan_f", 4096)
+        n = plan.int_host.numel()
+        ints[:n].copy_(plan.int_host, non_blocking=True)
+        S1 = plan.S + 1
+        fl[:2 * S1].copy_(plan.f_host.reshape(-1), non_blocking=True)
+        self.ix = {k: ints[o:o + ln] for k, (o, ln) in plan.int_layout.items()}
+        self.tuc, self.dt = fl[:S1], fl[S1:2 * S1]
+        E = self.nc * self.W0 * self.W0
+        coef = [1.0 / (self.B * E)] * plan.S + [self.opt["weight_cpc"] / (self.B * E)]
+        cf = self.fbuf("plan_coef", 256)
+        cf[:S1].copy_(torch.tensor(coef, dtype=torch.float64).float(), non_blocking=True)
+        self.coef = cf[:S1]
+
+    # ------------------------------------------------------------------ phases
+    def step(self, x, probs=None, eps=None, return_device=False):
+        """x: [T,B,C,H,W] fp32 on the device.  probs: host numpy uniform draws (None -> np.random.uniform,
+        like models/p2p_model.py:215).  eps: [S,2,B,z] N(0,1) (None -> torch.randn on the device)."""
+        T, B = int(x.shape[0]), int(x.shape[1])
+        opt = self.opt
+        if probs is None:
+            probs = np.random.uniform(0, 1, T - 1)
+        plan = StepPlan(T, probs, opt)
+        self.last_plan = plan
+        self.T, self.B, self.S = T, B, plan.S
+        if eps is None:
+            eps = torch.randn(plan.S, 2, B, self.z, device=self.dev, dtype=torch.float32)
+        self.eps = eps.contiguous()
+        self.upload_plan(plan)
+        self.pack_weights()
+        self.encode(x, plan)
+        self.recurrent_fwd(plan)
+        self.decode(plan)
+        self.losses_fwd(plan)
+        self.backward_main(plan)
+        if self.mode == "A":
+            self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
+            self.pack_weights(("decoder",))
+            self.backward_prior(plan)
+        else:
+            self.backward_prior(plan)
+            self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
+        self.adam(("prior",))
+        out = self._bufs["loss_out"][:4]
+        return out if return_device else out.cpu().numpy()
+
+    # -- Phase E ----------------------------------------------------------------------------
+    def encode(self, x, plan):
+        K, T, B, n, nc, W0 = self.K, self.T, self.B, self.n, self.nc, self.W0
+        P = self.arena["encoder"].p
+        N = T * B
+        # NCHW fp32 -> NHWC (fp32 target for the MSE, act-dtype input of c1)
+        hw = W0 * W0
+        xs = x.contiguous()
+        self.x_nhwc = self.fbuf("x_nhwc", N * hw * nc)
+        K.permute4(xs, self.x_nhwc, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
+        if self.adt == torch.float32:
+            a = self.x_nhwc
+        else:
+            a = self.buf("x_act", N * hw * nc)
+            K.permute4(xs, a, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
+        self.enc_in = a
+        self.enc = []
+        H = W0
+        for l in range(n):
+            cin = nc if l == 0 else self.chans[l - 1]
+            cout = self.chans[l]
+            Ho = H // 2
+            M = N * Ho * Ho
+            col = self.buf(f"enc_col{l}", M * 16 * cin)
+            raw = self.buf(f"enc_raw{l}", M * cout)
+            y = self.buf(f"enc_y{l}", M * cout)
+            cn, bn = self.enc_names(l)
+            K.im2col(a, col, N, H, H, cin)
+            K.gemm(col, self._packed[f"enc{l}"], raw, M, cout, 16 * cin, bias=P[cn + ".bias"])
+            st = self.bn_forward("enc", l, raw, y, T, B * Ho * Ho, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
+            self.enc.append(dict(col=col, raw=raw, y=y, st=st, cin=cin, cout=cout, Hin=H, Hout=Ho, M=M))
+            a, H = y, Ho
+        # final 4x4 valid conv == GEMM over the flattened 4x4xC map
+        ctop = self.chans[-1]
+        cn, bn = self.enc_names(n)
+        raw = self.buf("enc_rawf", N * self.g)
+        y = self.buf("enc_yf", N * self.g)
+        K.gemm(a, self._packed[f"enc{n}"], raw, N, self.g, 16 * ctop, bias=P[cn + ".bias"])
+        st = self.bn_forward("enc", n, raw, y, T, B, self.g, P[bn + ".weight"], P[bn + ".bias"], ACT_TANH)
+        self.enc_final = dict(inp=a, raw=raw, y=y, st=st)
+        if self.adt == torch.float32:
+            self.Hlat = y
+        else:
+            self.Hlat = self.fbuf("Hlat", N * self.g)
+            K.permute4(y, self.Hlat, (N * self.g, 1, 1, 1), (1, 0, 0, 0))
+        # running statistics: one EMA update per reference call, in call order
+        ncalls = len(plan.enc_order)
+        Bf = self.buffers["encoder"]
+        for l in range(n + 1):
+            st = self.enc[l]["st"] if l < n else self.enc_final["st"]
+            bn = self.enc_names(l)[1]
+            K.bn_ema(Bf[bn + ".running_mean"], Bf[bn + ".running_var"], st["mean"], st["varu"], self.ix["enc_order"], ncalls,
+                     st["C"], BN_MOMENTUM)
+            Bf[bn + ".num_batches_tracked"] += ncalls
+
+    def bn_forward(self, tag, idx, raw, y, G, R, C, gamma, beta, act):
+        K = self.K
+        names = ("mean", "invstd", "varu", "scale", "shift", "sdz", "sdzx")
+        st = {nm: self.fbuf(f"{tag}_bn{idx}_{nm}", G * C) for nm in names}
+        st.update(G=G, R=R, C=C, act=act, gamma=gamma)
+        K.bn_fwd_stats(raw, G, R, C, gamma, beta, st["mean"], st["invstd"], st["varu"], st["scale"], st["shift"])
+        K.bn_act(raw, y, st["scale"], st["shift"], G, R, C, act)
+        return st
+
+    # -- Phase R ----------------------------------------------------------------------------
+    def lstm_layers(self, m):
+        return len({k.split(".")[1] for k in self.arena[m].p if k.startswith("lstm.")})
+
+    def lstm_forward(self, m, X, steps, in_dim):
+        """embed -> n x LSTMCell over `steps` timesteps.  X: [steps*B, in_dim].  Returns the top layer's
+        hidden states [steps*B, R] (a view of the saved state)."""
+        K, B, R = self.K, self.B, self.R
+        P = self.arena[m].p
+        L = self.lstm_layers(m)
+        rows = steps * B
+        E = self.fbuf(f"{m}_E", rows * R)
+        K.gemm(X, P["embed.weight"], E, rows, R, in_dim, bias=P["embed.bias"])
+        sv = dict(X=X, E=E, steps=steps, in_dim=in_dim, layers=[])
+        inp = E
+        for l in range(L):
+            Pre = self.fbuf(f"{m}_pre{l}", rows * 4 * R)
+            gates = self.fbuf(f"{m}_gates{l}", rows * 4 * R)
+            hs = self.fbuf(f"{m}_h{l}", (steps + 1) * B * R)
+            cs = self.fbuf(f"{m}_c{l}", (steps + 1) * B * R)
+            hs[:B * R].zero_()
+            cs[:B * R].zero_()
+            K.gemm(inp, P[f"lstm.{l}.weight_ih"], Pre, rows, 4 * R, R, bias=P[f"lstm.{l}.bias_ih"])
+            whh, bhh = P[f"lstm.{l}.weight_hh"], P[f"lstm.{l}.bias_hh"]
+            for s in range(steps):
+                gs = gates[s * B * 4 * R:(s + 1) * B * 4 * R]
+                K.gemm(hs[s * B * R:(s + 1) * B * R], whh, gs, B, 4 * R, R, bias=bhh, addend=Pre[s * B * 4 * R:(s + 1) * B * 4 * R])
+                K.lstm_pointwise_fwd(gs, cs[s * B * R:(s + 1) * B * R], cs[(s + 1) * B * R:(s + 2) * B * R],
+                                     hs[(s + 1) * B * R:(s + 2) * B * R], B, R)
+            sv["layers"].append(dict(gates=gates, hs=hs, cs=cs, inp=inp))
+            inp = hs[B * R:(steps + 1) * B * R]
+        sv["top"] = inp
+        return sv
+
+    def recurrent_fwd(self, plan):
+        K, B, S, g, z, R = self.K, self.B, self.S, self.g, self.z, self.R
+        H = self.Hlat
+        ix = self.ix
+        win = 2 * g + 2
+        Xpost = self.fbuf("Xpost", S * B * win)
+        Xprior = self.fbuf("Xprior", S * B * win)
+        K.build_concat(Xpost, H, ix["tgt_idx"], g, H, ix["glob_idx"], g, self.tuc, self.dt, S, B)
+        K.build_concat(Xprior, H, ix["in_idx"], g, H, ix["glob_idx"], g, self.tuc, self.dt, S, B)
+        self.sv = {}
+        heads = {}
+        for m, X in (("posterior", Xpost), ("prior", Xprior)):
+            sv = self.lstm_forward(m, X, S, win)
+            P = self.arena[m].p
+            mu = self.fbuf(f"{m}_mu", S * B * z)
+            lv = self.fbuf(f"{m}_lv", S * B * z)
+            K.gemm(sv["top"], P["mu_net.weight"], mu, S * B, z, R, bias=P["mu_net.bias"])
+            K.gemm(sv["top"], P["logvar_net.weight"], lv, S * B, z, R, bias=P["logvar_net.bias"])
+            heads[m] = (mu, lv)
+            self.sv[m] = sv
+        self.mu, self.lv = heads["posterior"]
+        self.mu_p, self.lv_p = heads["prior"]
+        n = S * B * z
+        self.eps_post = self.fbuf("eps_post", n)
+        self.eps_prior = self.fbuf("eps_prior", n)
+        K.permute4(self.eps, self.eps_post, (S, B * z, 1, 1), (2 * B * z, 1, 0, 0))
+        K.permute4(self.eps[:, 1], self.eps_prior, (S, B * z, 1, 1), (2 * B * z, 1, 0, 0))
+        self.Zall = self.fbuf("Zall", (S + 1) * B * z)  # rows 0..S-1 posterior z, row S = prior z of the last step
+        self.Zp = self.fbuf("Zp", n)
+        self.kl_sum = self.fbuf("kl_sum", 4)
+        K.reparam_kl_fwd(self.mu, self.lv, self.mu_p, self.lv_p, self.eps_post, self.eps_prior, self.Zall, self.Zp, n, self.kl_sum)
+        K.permute4(self.Zp[(S - 1) * B * z:], self.Zall[S * B * z:], (B * z, 1, 1, 1), (1, 0, 0, 0))
+        # frame predictor over S recon steps + the CPC step (models/p2p_model.py:247,252)
+        wp = g + z + 2
+        Xpred = self.fbuf("Xpred", (S + 1) * B * wp)
+        K.build_concat(Xpred, H, ix["in_idx"], g, self.Zall, ix["z_idx"], z, self.tuc, self.dt, S + 1, B)
+        sv = self.lstm_forward("frame_predictor", Xpred, S + 1, wp)
+        self.sv["frame_predictor"] = sv
+        P = self.arena["frame_predictor"].p
+        self.h_pred = self.fbuf("h_pred", (S + 1) * B * g)
+        K.gemm(sv["top"], P["output.0.weight"], self.h_pred, (S + 1) * B, g, R, bias=P["output.0.bias"])
+        K.act_fwd(self.h_pred, (S + 1) * B * g, ACT_TANH)
+
+    # -- Phase D ----------------------------------------------------------------------------
+    def decode(self, plan):
+        K, B, S, n, g = self.K, self.B, self.S, self.n, self.g
+        G = S + 1
+        P = self.arena["decoder"].p
+        N = G * B
+        if self.adt == torch.float32:
+            hp = self.h_pred
+        else:
+            hp = self.buf("hp_act", N * g)
+            K.permute4(self.h_pred, hp, (N * g, 1, 1, 1), (1, 0, 0, 0))
+        ctop = self.chans[-1]
+        cn, bn = self.dec_names(-1)
+        raw = self.buf("dec_raw_1", N * 16 * ctop)
+        d = self.buf("dec_d_1", N * 16 * ctop)
+        K.gemm(hp, self._packed["dec-1"], raw, N, 16 * ctop, g, b_mn=True, bias=self._packed["dec-1.bias16"])
+        st = self.bn_forward("dec", -1, raw, d, G, B * 16, ctop, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
+        self.dec_first = dict(inp=hp, raw=raw, d=d, st=st)
+        self.dec = []
+        Hi = 4
+        nskip = plan.nskip
+        for k in range(n):
+            cd = self.chans[n - 1 - k]
+            cout = self.chans[n - 2 - k] if k < n - 1 else self.nc
+            skip = self.enc[n - 1 - k]["y"]  # frames are a prefix -> the first nskip frames
+            Md, Ms = N * Hi * Hi, nskip * B * Hi * Hi
+            wp = self._packed[f"dec{k}"]
+            wD, wS = wp[:cd * 16 * cout], wp[cd * 16 * cout:]
+            colD = self.buf("dec_colD", Md * 16 * cout)
+            colS = self.buf("dec_colS", Ms * 16 * cout)
+            K.gemm(d, wD, colD, Md, 16 * cout, cd, b_mn=True)
+            K.gemm(skip, wS, colS, Ms, 16 * cout, cd, b_mn=True)
+            cn, bn = self.dec_names(k)
+            Mo = N * 4 * Hi * Hi
+            raw = self.buf(f"dec_raw{k}", Mo * cout)
+            K.col2im(colD, raw, N, Hi, Hi, cout, bias=P[cn + ".bias"], col2=colS, grp_src=self.ix["skip_src"], imgs_per_group=B)
+            rec = dict(inp=d, skip=skip, raw=raw, cd=cd, cout=cout, Hi=Hi, Md=Md, Ms=Ms)
+            if k < n - 1:
+                dn = self.buf(f"dec_d{k}", Mo * cout)
+                rec["st"] = self.bn_forward("dec", k, raw, dn, G, B * 4 * Hi * Hi, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
+                rec["d"] = dn
+                d = dn
+            self.dec.append(rec)
+            Hi *= 2
+        Bf = self.buffers["decoder"]
+        for k in range(-1, n - 1):
+            st = self.dec_first["st"] if k < 0 else self.dec[k]["st"]
+            bn = self.dec_names(k)[1]
+            K.bn_ema(Bf[bn + ".running_mean"], Bf[bn + ".running_var"], st["mean"], st["varu"], self.ix["dec_order"], G, st["C"], BN_MOMENTUM)
+            Bf[bn + ".num_batches_tracked"] += G
+
+    def losses_fwd(self, plan):
+        K, B, S = self.K, self.B, self.S
+        G = S + 1
+        E = B * self.nc * self.W0 * self.W0
+        raw = self.dec[-1]["raw"]
+        self.d_rawout = self.buf("dec_d_rawout", G * E)
+        self.mse_partial = self.fbuf("mse_partial", G * K.mse_chunks())
+        K.sigmoid_mse(raw, self.x_nhwc, self.ix["tgt_idx"], self.coef, G, E, None, self.d_rawout, self.mse_partial)
+        self.align_partial = self.fbuf("align_partial", max(S, 1))
+        self.d_hpred = self.fbuf("d_hpred", G * B * self.g)
+        self.dH = self.fbuf("dH", self.T * B * self.g)
+
+    # -- backward ---------------------------------------------------------------------------
+    def decoder_backward(self, g0, g1, want_wgrad, want_skip):
+        """Backward of the decoder calls [g0, g1).  Seeds: d_rawout.  Produces d_hpred[g0:g1] (fp32) and,
+        if requested, weight gradients (into the decoder grad arena) and the skip gradients."""
+        K, B, n, g = self.K, self.B, self.n, self.g
+        Gn = g1 - g0
+        N = Gn * B
+        A = self.arena["decoder"]
+        nskip = self.last_plan.nskip
+        E = self.nc * self.W0 * self.W0
+        dy = self.d_rawout[g0 * B * E:g1 * B * E]
+        for k in range(n - 1, -1, -1):
+            rec = self.dec[k]
+            cd, cout, Hi = rec["cd"], rec["cout"], rec["Hi"]
+            Md, Ms = N * Hi * Hi, nskip * B * Hi * Hi
+            cn, bn = self.dec_names(k)
+            Ho = 2 * Hi
+            rows_o = N * Ho * Ho
+            if k < n - 1:  # BatchNorm + LeakyReLU backward of this stage's output
+                st = rec["st"]
+                sl = slice(g0 * B * Ho * Ho * cout, g1 * B * Ho * Ho * cout)
+                c0, c1 = g0 * st["C"], g1 * st["C"]
+                K.bn_bwd(dy, rec["raw"][sl], rec["d"][sl], st["mean"][c0:c1], st["invstd"][c0:c1], st["gamma"], Gn,
+                         B * Ho * Ho, cout, ACT_LRELU, dy, st["sdz"][c0:c1], st["sdzx"][c0:c1])
+                if want_wgrad:
+                    K.bn_param_grad(st["sdz"][c0:c1], st["sdzx"][c0:c1], Gn, cout, A.g[bn + ".weight"], A.g[bn + ".bias"])
+            if want_wgrad:
+                K.colsum(dy, rows_o, cout, cout, A.g[cn + ".bias"])
+            dcol = self.buf("scratch_dcol", Md * 16 * cout)
+            K.im2col(dy, dcol, N, Ho, Ho, cout)
+            wp = self._packed[f"dec{k}"]
+            wD, wS = wp[:cd * 16 * cout], wp[cd * 16 * cout:]
+            x_in = rec["inp"][g0 * B * Hi * Hi * cd:g1 * B * Hi * Hi * cd]
+            dd = self.buf(f"dec_gd{k}", Md * cd)
+            K.gemm(dcol, wD, dd, Md, cd, 16 * cout)
+            if want_wgrad:
+                gw = self.fbuf(f"gwp_dec{k}", 2 * cd * 16 * cout)
+                K.gemm(x_in, dcol, gw[:cd * 16 * cout], cd, 16 * cout, Md, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
+            if want_skip:
+                dcolS = self.buf("scratch_dcolS", Ms * 16 * cout)
+                K.group_sum(dcol, dcolS, self.ix["skip_src"][g0:g1], Gn, nskip, B * Hi * Hi * 16 * cout)
+                dsk = self.buf(f"dskip{k}", Ms * cd)
+                K.gemm(dcolS, wS, dsk, Ms, cd, 16 * cout)
+                rec["dskip"] = dsk
+                if want_wgrad:
+                    K.gemm(rec["skip"], dcolS, gw[cd * 16 * cout:], cd, 16 * cout, Ms, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
+            if want_wgrad:
+                K.permute4(gw, A.g[cn + ".weight"], (2 * cd, cout, 4, 4), (16 * cout, 1, 4 * cout, cout))
+            dy = dd
+        # upc1: BatchNorm + LeakyReLU, then the g -> 4x4xCtop GEMM
+        ctop = self.chans[-1]
+        cn, bn = self.dec_names(-1)
+        st = self.dec_first["st"]
+        sl = slice(g0 * B * 16 * ctop, g1 * B * 16 * ctop)
+        c0, c1 = g0 * ctop, g1 * ctop
+        K.bn_bwd(dy, self.dec_first["raw"][sl], self.dec_first["d"][sl], st["mean"][c0:c1], st["invstd"][c0:c1], st["gamma"], Gn,
+                 B * 16, ctop, ACT_LRELU, dy, st["sdz"][c0:c1], st["sdzx"][c0:c1])
+        hp = self.dec_first["inp"][g0 * B * g:g1 * B * g]
+        if want_wgrad:
+            K.bn_param_grad(st["sdz"][c0:c1], st["sdzx"][c0:c1], Gn, ctop, A.g[bn + ".weight"], A.g[bn + ".bias"])
+            K.colsum(dy, N * 16, ctop, ctop, A.g[cn + ".bias"])
+            gw = self.fbuf("gwp_dec-1", g * 16 * ctop)
+            K.gemm(hp, dy, gw, g, 16 * ctop, N, a_mn=True, b_mn=True, lda=g, ldb=16 * ctop)
+            K.permute4(gw, A.g[cn + ".weight"], (g, ctop, 4, 4), (16 * ctop, 1, 4 * ctop, ctop))
+        dhp = self.d_hpred[g0 * B * g:g1 * B * g]
+        if self.adt == torch.float32:
+            K.gemm(dy, self._packed["dec-1"], dhp, N, g, 16 * ctop)
+        else:
+            tmp = self.buf("dhp_act", N * g)
+            K.gemm(dy, self._packed["dec-1"], tmp, N, g, 16 * ctop)
+            K.permute4(tmp, dhp, (N * g, 1, 1, 1), (1, 0, 0, 0))
+
+    def lstm_backward(self, m, dtop, steps, want_wgrad, want_dx, dx_out=None):
+        """Reverse-time scan.  dtop: [steps*B, R] gradient w.r.t. the top layer's hidden outputs (it is
+        overwritten).  Returns dX [steps*B, in_dim] if want_dx."""
+        K, B, R = self.K, self.B, self.R
+        sv = self.sv[m]
+        A = self.arena[m]
+        P = A.p
+        L = len(sv["layers"])
+        rows = steps * B
+        dH = dtop
+        for l in range(L - 1, -1, -1):
+            lay = sv["layers"][l]
+            dG = self.fbuf(f"{m}_dG{l}", rows * 4 * R)
+            dcA = self.fbuf(f"{m}_dcA", B * R)
+            dcB = self.fbuf(f"{m}_dcB", B * R)
+            dht = self.fbuf(f"{m}_dht", B * R)
+            whh = P[f"lstm.{l}.weight_hh"]
+            dc_next = None
+            for s in range(steps - 1, -1, -1):
+                dh_s = dH[s * B * R:(s + 1) * B * R]
+                if s < steps - 1:
+                    # dh_total = dH[s] + dG[s+1] . W_hh
+                    K.gemm(dG[(s + 1) * B * 4 * R:(s + 2) * B * 4 * R], whh, dht, B, R, 4 * R, b_mn=True, addend=dh_s)
+                    dh_s = dht
+                dc_prev = dcA if (s % 2 == 0) else dcB
+                K.lstm_pointwise_bwd(dh_s, dc_next, lay["gates"][s * B * 4 * R:(s + 1) * B * 4 * R],
+                                     lay["cs"][s * B * R:(s + 1) * B * R], lay["cs"][(s + 1) * B * R:(s + 2) * B * R],
+                                     dG[s * B * 4 * R:(s + 1) * B * 4 * R], dc_prev, B, R)
+                dc_next = dc_prev
+            if want_wgrad:
+                K.gemm(dG, lay["hs"], A.g[f"lstm.{l}.weight_hh"], 4 * R, R, rows, a_mn=True, b_mn=True, lda=4 * R, ldb=R)
+                K.gemm(dG, lay["inp"], A.g[f"lstm.{l}.weight_ih"], 4 * R, R, rows, a_mn=True, b_mn=True, lda=4 * R, ldb=R)
+                K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_ih"])
+                K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_hh"])
+            dIn = self.fbuf(f"{m}_dIn{l}", rows * R)
+            K.gemm(dG, P[f"lstm.{l}.weight_ih"], dIn, rows, R, 4 * R, b_mn=True)
+            dH = dIn
+        dE = dH
+        in_dim = sv["in_dim"]
+        if want_wgrad:
+            K.gemm(dE, sv["X"], A.g["embed.weight"], R, in_dim, rows, a_mn=True, b_mn=True, lda=R, ldb=in_dim)
+            K.colsum(dE, rows, R, R, A.g["embed.bias"])
+        if want_dx:
+            dX = dx_out if dx_out is not None else self.fbuf(f"{m}_dX", rows * in_dim)
+            K.gemm(dE, P["embed.weight"], dX, rows, in_dim, R, b_mn=True)
+            return dX
+        return None
+
+    def gaussian_heads_backward(self, m, dmu, dlv, steps, want_wgrad):
+        K, B, R, z = self.K, self.B, self.R, self.z
+        A = self.arena[m]
+        rows = steps * B
+        top = self.sv[m]["top"]
+        dtop = self.fbuf(f"{m}_dtop", rows * R)
+        K.gemm(dmu, A.p["mu_net.weight"], dtop, rows, R, z, b_mn=True)
+        K.gemm(dlv, A.p["logvar_net.weight"], dtop, rows, R, z, b_mn=True, accumulate=True)
+        if want_wgrad:
+            K.gemm(dmu, top, A.g["mu_net.weight"], z, R, rows, a_mn=True, b_mn=True, lda=z, ldb=R)
+            K.gemm(dlv, top, A.g["logvar_net.weight"], z, R, rows, a_mn=True, b_mn=True, lda=z, ldb=R)
+            K.colsum(dmu, rows, z, z, A.g["mu_net.bias"])
+            K.colsum(dlv, rows, z, z, A.g["logvar_net.bias"])
+        return dtop
+
+    def backward_main(self, plan):
+        """loss = mse + beta*kld + weight_align*align  (models/p2p_model.py:261-262)."""
+        K, B, S, g, z, R, T = self.K, self.B, self.S, self.g, self.z, self.R, self.T
+        opt = self.opt
+        self.d_hpred[:(S + 1) * B * g].zero_()
+        self.dH[:T * B * g].zero_()
+        self.decoder_backward(0, S, want_wgrad=True, want_skip=True)
+        # alignment loss (value + gradients into d_hpred / dH)
+        K.align(self.Hlat, self.ix["in_idx"], self.h_pred, S - 1, B, g, float(opt["weight_align"]), self.align_partial,
+                self.d_hpred, self.dH)
+        # the four scalars
+        self.loss_out = self.fbuf("loss_out", 4)
+        E = B * self.nc * self.W0 * self.W0
+        K.finalize_losses(self.mse_partial, S, plan.has_cpc, E, self.kl_sum, float(opt["batch_size"]), self.align_partial,
+                          max(S - 1, 0), float(T), self.loss_out)
+        # frame predictor (recon steps only; the CPC step has no cotangent in this pass)
+        A = self.arena["frame_predictor"]
+        rows = S * B
+        dpre = self.fbuf("pred_dpre", (S + 1) * B * g)
+        K.act_bwd(self.d_hpred, self.h_pred, dpre, rows * g, ACT_TANH)
+        top = self.sv["frame_predictor"]["top"]
+        K.gemm(dpre, top, A.g["output.0.weight"], g, R, rows, a_mn=True, b_mn=True, lda=g, ldb=R)
+        K.colsum(dpre, rows, g, g, A.g["output.0.bias"])
+        dtop = self.fbuf("pred_dtop", (S + 1) * B * R)
+        K.gemm(dpre, A.p["output.0.weight"], dtop, rows, R, g, b_mn=True)
+        wp = g + z + 2
+        dXpred = self.lstm_backward("frame_predictor", dtop, S, want_wgrad=True, want_dx=True)
+        # posterior / prior seeds: d z_post from the predictor input, beta * dKL
+        dz = self.fbuf("dz_post", S * B * z)
+        K.permute4(dXpred[g:], dz, (S * B, z, 1, 1), (wp, 1, 0, 0))
+        n = S * B * z
+        dmu, dlv, dmu_p, dlv_p = (self.fbuf(nm, n) for nm in ("dmu", "dlv", "dmu_p", "dlv_p"))
+        K.reparam_kl_bwd(self.mu, self.lv, self.mu_p, self.lv_p, self.eps_post, self.eps_prior, dz, None,
+                         float(opt["beta"]) / float(opt["batch_size"]), dmu, dlv, dmu_p, dlv_p, n)
+        win = 2 * g + 2
+        dtop = self.gaussian_heads_backward("posterior", dmu, dlv, S, want_wgrad=True)
+        dXpost = self.lstm_backward("posterior", dtop, S, want_wgrad=True, want_dx=True)
+        dtop = self.gaussian_heads_backward("prior", dmu_p, dlv_p, S, want_wgrad=False)
+        dXprior = self.lstm_backward("prior", dtop, S, want_wgrad=False, want_dx=True)
+        # latent gradients -> dH[T,B,g]
+        ix = self.ix
+        K.gather_add_cols(self.dH, dXpost, ix["tgt_idx"], S, T, B, g, win, 0)
+        K.gather_add_cols(self.dH, dXpost, ix["glob_idx"], S, T, B, g, win, g)
+        K.gather_add_cols(self.dH, dXprior, ix["in_idx"], S, T, B, g, win, 0)
+        K.gather_add_cols(self.dH, dXprior, ix["glob_idx"], S, T, B, g, win, g)
+        K.gather_add_cols(self.dH, dXpred, ix["in_idx"], S, T, B, g, wp, 0)
+        self.encoder_backward(plan)
+
+    def encoder_backward(self, plan):
+        K, T, B, n, g = self.K, self.T, self.B, self.n, self.g
+        A = self.arena["encoder"]
+        N = T * B
+        nskip = plan.nskip
+        if self.adt == torch.float32:
+            dy = self.dH
+        else:
+            dy = self.buf("dH_act", N * g)
+            K.permute4(self.dH, dy, (N * g, 1, 1, 1), (1, 0, 0, 0))
+        cn, bn = self.enc_names(n)
+        fin = self.enc_final
+        st = fin["st"]
+        K.bn_bwd(dy, fin["raw"], fin["y"], st["mean"], st["invstd"], st["gamma"], T, B, g, ACT_TANH, dy, st["sdz"], st["sdzx"])
+        K.bn_param_grad(st["sdz"], st["sdzx"], T, g, A.g[bn + ".weight"], A.g[bn + ".bias"])
+        K.colsum(dy, N, g, g, A.g[cn + ".bias"])
+        ctop = self.chans[-1]
+        gw = self.fbuf(f"gwp_enc{n}", g * 16 * ctop)
+        K.gemm(dy, fin["inp"], gw, g, 16 * ctop, N, a_mn=True, b_mn=True, lda=g, ldb=16 * ctop)
+        K.permute4(gw, A.g[cn + ".weight"], (g, ctop, 4, 4), (16 * ctop, 1, 4 * ctop, ctop))
+        gy = self.buf(f"enc_gy{n - 1}", N * 16 * ctop)
+        K.gemm(dy, self._packed[f"enc{n}"], gy, N, 16 * ctop, g, b_mn=True)
+        for l in range(n - 1, -1, -1):
+            rec = self.enc[l]
+            cin, cout, M, Ho = rec["cin"], rec["cout"], rec["M"], rec["Hout"]
+            # skip-connection gradient from the decoder stage that consumed this layer's output
+            k = n - 1 - l
+            dsk = self.dec[k].get("dskip")
+            if dsk is not None:
+                K.add_indexed(gy, dsk, self.ix["skip_dst"], nskip, B * Ho * Ho * cout)
+            cn, bn = self.enc_names(l)
+            st = rec["st"]
+            K.bn_bwd(gy, rec["raw"], rec["y"], st["mean"], st["invstd"], st["gamma"], T, B * Ho * Ho, cout, ACT_LRELU, gy,
+                     st["sdz"], st["sdzx"])
+            K.bn_param_grad(st["sdz"], st["sdzx"], T, cout, A.g[bn + ".weight"], A.g[bn + ".bias"])
+            K.colsum(gy, M, cout, cout, A.g[cn + ".bias"])
+            gw = self.fbuf(f"gwp_enc{l}", cout * 16 * cin)
+            K.gemm(gy, rec["col"], gw, cout, 16 * cin, M, a_mn=True, b_mn=True, lda=cout, ldb=16 * cin)
+            K.permute4(gw, A.g[cn + ".weight"], (cout, cin, 4, 4), (16 * cin, 1, 4 * cin, cin))
+            if l > 0:
+                dcol = self.buf("scratch_dcol", M * 16 * cin)
+                K.gemm(gy, self._packed[f"enc{l}"], dcol, M, 16 * cin, cout, b_mn=True)
+                gprev = self.buf(f"enc_gy{l - 1}", N * rec["Hin"] * rec["Hin"] * cin)
+                K.col2im(dcol, gprev, N, Ho, Ho, cin)
+                gy = gprev
+
+    def backward_prior(self, plan):
+        """prior_loss = kld + weight_cpc*cpc (models/p2p_model.py:266-268): CPC chain through decoder and
+        frame predictor (their *current* weights), then BPTT through the prior with weight gradients."""
+        K, B, S, g, z, R = self.K, self.B, self.S, self.g, self.z, self.R
+        opt = self.opt
+        n = S * B * z
+        dzp = self.fbuf("dz_prior", n)
+        dzp[:n].zero_()
+        if plan.has_cpc:
+            self.decoder_backward(S, S + 1, want_wgrad=False, want_skip=False)
+            A = self.arena["frame_predictor"]
+            sv = self.sv["frame_predictor"]
+            dpre = self.fbuf("cpc_dpre", B * g)
+            K.act_bwd(self.d_hpred[S * B * g:], self.h_pred[S * B * g:], dpre, B * g, ACT_TANH)
+            dh = self.fbuf("cpc_dh", B * R)
+            K.gemm(dpre, A.p["output.0.weight"], dh, B, R, g, b_mn=True)
+            L = len(sv["layers"])
+            dG = self.fbuf("cpc_dG", B * 4 * R)
+            dcp = self.fbuf("cpc_dc", B * R)
+            for l in range(L - 1, -1, -1):
+                lay = sv["layers"][l]
+                K.lstm_pointwise_bwd(dh, None, lay["gates"][S * B * 4 * R:(S + 1) * B * 4 * R], lay["cs"][S * B * R:(S + 1) * B * R],
+                                     lay["cs"][(S + 1) * B * R:(S + 2) * B * R], dG, dcp, B, R)
+                dh2 = self.fbuf(f"cpc_dh{l}", B * R)
+                K.gemm(dG, A.p[f"lstm.{l}.weight_ih"], dh2, B, R, 4 * R, b_mn=True)
+                dh = dh2
+            wp = g + z + 2
+            dX = self.fbuf("cpc_dX", B * wp)
+            K.gemm(dh, A.p["embed.weight"], dX, B, wp, R, b_mn=True)
+            K.permute4(dX[g:], dzp[(S - 1) * B * z:], (B, z, 1, 1), (wp, 1, 0, 0))
+        dmu, dlv, dmu_p, dlv_p = (self.fbuf(nm, n) for nm in ("dmu", "dlv", "dmu_p", "dlv_p"))
+        K.reparam_kl_bwd(self.mu, self.lv, self.mu_p, self.lv_p, self.eps_post, self.eps_prior, None, dzp,
+                         1.0 / float(opt["batch_size"]), dmu, dlv, dmu_p, dlv_p, n)
+        dtop = self.gaussian_heads_backward("prior", dmu_p, dlv_p, S, want_wgrad=True)
+        self.lstm_backward("prior", dtop, S, want_wgrad=True, want_dx=False)
+
+    # -- optimiser --------------------------------------------------------------------------
+    def adam(self, modules):
+        opt = self.opt
+        for m in modules:
+            A = self.arena[m]
+            A.step_t += 1
+            self.K.adam(A.flat, A.grad, A.m, A.v, A.numel, float(opt["lr"]), float(opt["beta1"]), 0.999, 1e-8, A.step_t)
+
+    # -- export -----------------------------------------------------------------------------
+    def state_dict(self, m):
+        out = OrderedDict()
+        for k in self.arena[m].names:
+            out[k] = self.arena[m].p[k]
+        out.update(self.buffers[m])
+        return out
