@@ -65,6 +65,7 @@ int p2pvg_adam_legacy_impl(float*, const float*, float*, float*, long long, doub
 int p2pvg_scale_impl(float*, long long, float, cudaStream_t);
 
 static int g_gemm_impl = 0;  // 0 auto, 1 simt, 2 tcgen05
+int p2pvg_gemm_impl_forced() { return g_gemm_impl; }
 
 #define ST ((cudaStream_t)stream)
 

@@ -1,7 +1,435 @@
+// bf16 GEMM on the 5th-generation tensor cores (sm_100a): TMA (cp.async.bulk.tensor) stages 128B-swizzled
+// operand tiles in shared memory, one elected thread issues tcgen05.mma (cta_group::1, kind::f16) with the
+// fp32 accumulator in TMEM, four epilogue warps read it back with tcgen05.ld and store.
+//
+//   C[M,N] = (accumulate ? C : 0) + opA(A)*opB(B) + bias[n] + addend[m,n]          (same contract as gemm_simt)
+//
+// Operands may be K-major (row = m or n, contiguous along k) or MN-major (row = k, contiguous along m / n);
+// MN-major tiles are what the weight-gradient GEMMs (reduction over pixels of NHWC tensors) need, so no
+// transposed copies of activations are ever materialised.  Split-K (grid.z) with a deterministic second
+// pass covers the weight gradients, whose output is tiny and whose reduction dimension is huge.
+//
+// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
-int p2pvg_gemm_tc_available() { return 0; }
-int p2pvg_gemm_tc(const void*, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int, const float*,
-                  const void*, long long, void*, size_t, cudaStream_t) {
-  p2pvg_set_error("gemm_tc: stub");
-  return P2PVG_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 192;
+
+template <int BN> struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* desc, uint64_t* bar, void* smem_dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version bit set)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version for tcgen05
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv,
+               int c_bf16, long long ldc, int M, int N, int K, int accumulate, const float* __restrict__ bias,
+               const void* __restrict__ addend, long long ldd, float* __restrict__ partial, int kb_per_split) {
+  using C_ = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C_::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C_::STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BN;
+  const int nkb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int kb1 = min(kb0 + kb_per_split, nkb_total);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C_::STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % C_::STAGES;
+        const uint32_t ph = (i / C_::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * C_::STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
+        const int k0 = (kb0 + i) * BLOCK_K;
+        if (A_MN) {
+          tma_load_2d(&tmA, &full_bar[s], sa, m0, k0);
+          tma_load_2d(&tmA, &full_bar[s], sa + BLOCK_K * 128, m0 + 64, k0);
+        } else {
+          tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; j++) tma_load_2d(&tmB, &full_bar[s], sb + j * BLOCK_K * 128, n0 + 64 * j, k0);
+        } else {
+          tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % C_::STAGES;
+        const uint32_t ph = (i / C_::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+          // K-major: 16 bf16 = 32 B further inside the 128 B swizzle row; MN-major: 16 rows of 128 B further
+          const uint64_t da = A_MN ? make_desc(sa + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sa + k * UMMA_K * 2, 0, 1024);
+          const uint64_t db = B_MN ? make_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sb + k * UMMA_K * 2, 0, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const long long m = (long long)m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const bool row_ok = m < M;
+    const bool split = (partial != nullptr);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int nbase = n0 + c * 32;
+      if (!row_ok || nbase >= N) continue;
+      if (nkb <= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = 0u;
+      }
+      if (split) {
+        float* dst = partial + ((long long)blockIdx.z * M + m) * N + nbase;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (nbase + j < N) dst[j] = __uint_as_float(v[j]);
+        continue;
+      }
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (nbase + j < N) f[j] += bias[nbase + j];
+      }
+      if (c_bf16) {
+        bf16* crow = reinterpret_cast<bf16*>(Cv) + m * ldc + nbase;
+        if (addend) {
+          const bf16* arow = reinterpret_cast<const bf16*>(addend) + m * ldd + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (nbase + j < N) f[j] += __bfloat162float(arow[j]);
+        }
+        if (accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (nbase + j < N) f[j] += __bfloat162float(crow[j]);
+        }
+        const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(crow + j) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (nbase + j < N) crow[j] = __float2bfloat16_rn(f[j]);
+        }
+      } else {
+        float* crow = reinterpret_cast<float*>(Cv) + m * ldc + nbase;
+        if (addend) {
+          const float* arow = reinterpret_cast<const float*>(addend) + m * ldd + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (nbase + j < N) f[j] += arow[j];
+        }
+        if (accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (nbase + j < N) f[j] += crow[j];
+        }
+        const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (nbase + j < N) crow[j] = f[j];
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// second pass of split-K: C = sum_z partial[z] + bias + addend + (accumulate ? C : 0)
+template <typename TO>
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, TO* __restrict__ C, long long ldc, int M, int N,
+                                     int accumulate, const float* __restrict__ bias, const TO* __restrict__ addend, long long ldd) {
+  const long long total = (long long)M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / N;
+    const int n = (int)(idx - m * N);
+    float acc = 0.f;
+    for (int z = 0; z < splits; z++) acc += partial[(long long)z * total + idx];
+    if (bias) acc += bias[n];
+    if (addend) acc += ld_f<TO>(&addend[m * ldd + n]);
+    if (accumulate) acc += ld_f<TO>(&C[m * ldc + n]);
+    st_f<TO>(&C[m * ldc + n], acc);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_once;
+int g_attr_done[2][2][2] = {};
+
+void resolve_driver() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  (void)cudaGetLastError();
+}
+
+// 2-D bf16 tensor map: dim0 (contiguous) x dim1, row pitch ld elements, box (64 x box1), 128B swizzle, zero OOB fill
+int make_map(CUtensorMap* map, const void* base, long long dim0, long long dim1, long long ld, int box1) {
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    p2pvg_set_error("cuTensorMapEncodeTiled failed (%d): base=%p dims=(%lld,%lld) ld=%lld box1=%d", (int)r, base, dim0, dim1, ld, box1);
+    return P2PVG_ERR_CUDA;
+  }
+  return P2PVG_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, int M, int N, int K, int accumulate,
+           const float* bias, const void* addend, long long ldd, float* partial, int splits, int kb_per_split, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  int& done = g_attr_done[BN == 128][A_MN][B_MN];
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      p2pvg_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return P2PVG_ERR_CUDA;
+    }
+    done = 1;
+  }
+  dim3 grid(cdiv(M, BLOCK_M), cdiv(N, BN), splits);
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, C, c_dtype == P2PVG_BF16, ldc, M, N, K, accumulate, bias, addend, ldd,
+                                                      partial, kb_per_split);
+  return p2pvg_check_launch("gemm_tc");
+}
+
+}  // namespace
+
+int p2pvg_gemm_tc_available() {
+  std::call_once(g_once, resolve_driver);
+  return g_encode != nullptr;
+}
+
+int p2pvg_gemm_simt(const void*, int, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int,
+                    const float*, const void*, long long, cudaStream_t);
+
+static bool tc_operand_ok(const void* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 8 == 0); }
+
+int p2pvg_gemm_tc(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* C, int c_dtype, long long ldc,
+                  int M, int N, int K, int accumulate, const float* bias, const void* addend, long long ldd, void* workspace,
+                  size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return P2PVG_OK;
+  extern int p2pvg_gemm_impl_forced();
+  if (!p2pvg_gemm_tc_available() || !tc_operand_ok(A, lda) || !tc_operand_ok(B, ldb) || K <= 0) {
+    if (p2pvg_gemm_impl_forced() == 2) {
+      p2pvg_set_error("gemm_tc: operands not TMA-compatible (A=%p lda=%lld B=%p ldb=%lld K=%d, driver=%d)", A, lda, B, ldb, K,
+                      p2pvg_gemm_tc_available());
+      return P2PVG_ERR_UNSUPPORTED;
+    }
+    return p2pvg_gemm_simt(A, P2PVG_BF16, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, st);
+  }
+  const int BN = (N > 64) ? 128 : 64;
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn) rc = make_map(&ta, A, M, K, lda, BLOCK_K);
+  else rc = make_map(&ta, A, K, M, lda, BLOCK_M);
+  if (rc) return rc;
+  if (b_mn) rc = make_map(&tb, B, N, K, ldb, BLOCK_K);
+  else rc = make_map(&tb, B, K, N, ldb, BN);
+  if (rc) return rc;
+
+  // split-K when the output has too few tiles to fill the 148 SMs and the reduction is long
+  const int nkb = cdiv(K, BLOCK_K);
+  const long long tiles = (long long)cdiv(M, BLOCK_M) * cdiv(N, BN);
+  int splits = 1;
+  if (tiles < 120 && nkb >= 16) {
+    long long want = (2 * 148 + tiles - 1) / tiles;
+    long long maxs = nkb / 8;
+    splits = (int)(want < maxs ? want : maxs);
+    if (splits < 1) splits = 1;
+    size_t need = (size_t)splits * M * N * sizeof(float);
+    while (splits > 1 && (workspace == nullptr || need > ws_bytes)) {
+      splits /= 2;
+      need = (size_t)splits * M * N * sizeof(float);
+    }
+  }
+  int kb_per_split = cdiv(nkb, splits);
+  splits = cdiv(nkb, kb_per_split);
+  float* partial = splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
+
+#define GO(BN_, AM, BM)                                                                                                     \
+  rc = launch<BN_, AM, BM>(ta, tb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, partial, splits, kb_per_split, st)
+  if (BN == 128) {
+    if (a_mn && b_mn) GO(128, true, true);
+    else if (a_mn) GO(128, true, false);
+    else if (b_mn) GO(128, false, true);
+    else GO(128, false, false);
+  } else {
+    if (a_mn && b_mn) GO(64, true, true);
+    else if (a_mn) GO(64, true, false);
+    else if (b_mn) GO(64, false, true);
+    else GO(64, false, false);
+  }
+#undef GO
+  if (rc) return rc;
+  if (splits > 1) {
+    long long total = (long long)M * N;
+    int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+    if (c_dtype == P2PVG_BF16)
+      splitk_reduce_kernel<bf16><<<blocks, 256, 0, st>>>(partial, splits, (bf16*)C, ldc, M, N, accumulate, bias, (const bf16*)addend, ldd);
+    else
+      splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>(partial, splits, (float*)C, ldc, M, N, accumulate, bias, (const float*)addend, ldd);
+    return p2pvg_check_launch("splitk_reduce");
+  }
+  return P2PVG_OK;
 }

@@ -59,6 +59,59 @@ def test_gemm_simt(KS, impl, dtype, a_mn, b_mn, M, N, K):
         Kc.set_gemm_impl("auto")
 
 
+TC_SHAPES = [
+    # M, N, K, a_mn, b_mn
+    (128, 128, 64, False, False), (256, 128, 256, False, False), (300, 200, 136, False, False),
+    (128, 64, 64, False, False), (70, 16, 128, False, False), (1000, 48, 72, False, False),
+    (256, 128, 128, False, True), (192, 4096, 128, False, True), (130, 16, 128, False, True),
+    (128, 128, 128, True, True), (64, 1024, 4096, True, True), (512, 136, 1000, True, True), (128, 16, 3000, True, True),
+    (256, 128, 64, True, False), (100, 72, 200, True, False),
+    (128, 128, 16, False, False), (2048, 64, 16, False, False), (64, 1024, 100000, True, True),
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", TC_SHAPES)
+def test_gemm_tcgen05(KS, M, N, K, a_mn, b_mn):
+    Kc, Ke = KS
+    assert Kc.has_tcgen05(), "driver entry point cuTensorMapEncodeTiled not available"
+    Kc.set_gemm_impl("tc")
+    try:
+        dt = torch.bfloat16
+        A = rnd(K, M, dtype=dt, seed=21) if a_mn else rnd(M, K, dtype=dt, seed=21)
+        B = rnd(K, N, dtype=dt) if b_mn else rnd(N, K, dtype=dt)
+        bias = rnd(N)
+        for cdt in (torch.float32, torch.bfloat16):
+            add = rnd(M, N, dtype=cdt)
+            C1 = rnd(M, N, dtype=cdt)
+            C2 = C1.clone()
+            Kc.gemm(A, B, C1, M, N, K, a_mn=a_mn, b_mn=b_mn)
+            Ke.gemm(A, B, C2, M, N, K, a_mn=a_mn, b_mn=b_mn)
+            tol = dict(rtol=2e-3, atol=2e-3 * K ** 0.5) if cdt == torch.float32 else dict(rtol=1.6e-2, atol=1e-2 * K ** 0.5)
+            close(C1, C2, cdt, what="plain", **tol)
+            Kc.gemm(A, B, C1, M, N, K, a_mn=a_mn, b_mn=b_mn, accumulate=True, bias=bias, addend=add)
+            Ke.gemm(A, B, C2, M, N, K, a_mn=a_mn, b_mn=b_mn, accumulate=True, bias=bias, addend=add)
+            close(C1, C2, cdt, what="acc+bias+addend", **tol)
+    finally:
+        Kc.set_gemm_impl("auto")
+
+
+def test_gemm_tcgen05_strided_views(KS):
+    """Sub-matrix operands (leading dimension > extent), as the engine uses for packed weight halves."""
+    Kc, Ke = KS
+    Kc.set_gemm_impl("tc")
+    try:
+        big = rnd(512, 256, dtype=torch.bfloat16, seed=22)
+        A = big[:, 64:]          # [512, 192] with lda = 256  (offset 128 B: 16-byte aligned)
+        Bm = rnd(96, 192, dtype=torch.bfloat16)
+        C1 = torch.zeros(512, 96, device="cuda")
+        C2 = torch.zeros_like(C1)
+        Kc.gemm(A, Bm, C1, 512, 96, 192, lda=256)
+        Ke.gemm(A, Bm, C2, 512, 96, 192, lda=256)
+        close(C1, C2, rtol=2e-3, atol=3e-2)
+    finally:
+        Kc.set_gemm_impl("auto")
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("N,H,C", [(3, 8, 64), (2, 16, 1), (2, 8, 3), (1, 64, 4)])
 def test_im2col_col2im(KS, dtype, N, H, C):
