@@ -86,10 +86,8 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
   P2PVG_REQUIRE(A && B && C, P2PVG_ERR_BAD_ARG, "gemm: null operand");
   P2PVG_REQUIRE(M >= 0 && N >= 0 && K >= 0, P2PVG_ERR_BAD_ARG, "gemm: negative size");
   bool want_tc = (in_dtype == P2PVG_BF16) && g_gemm_impl != 1;
-  if (g_gemm_impl == 2 && in_dtype != P2PVG_BF16) {
-    p2pvg_set_error("gemm: tcgen05 path needs bf16 operands");
-    return P2PVG_ERR_UNSUPPORTED;
-  }
+  // fp32 operands (LSTM / parity mode) always run on the CUDA cores; "forced tcgen05" only makes the bf16 path
+  // refuse to fall back when an operand is not TMA-compatible.
   if (want_tc)
     return p2pvg_gemm_tc(A, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace, ws_bytes, ST);
   return p2pvg_gemm_simt(A, in_dtype, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, ST);

@@ -140,6 +140,8 @@ class TrainEngine:
             self.buffers[m] = {k: v.detach().clone().to(self.dev) for k, v in state[m].items() if not is_param_key(k)}
         self._bufs = {}
         self._packed = {}
+        self._graphs = {}
+        self.dist = None  # (torch.distributed, group, world_size) when batch-sharded over several GPUs
         self.last_plan = None
 
     # ------------------------------------------------------------------ memory
@@ -211,7 +213,7 @@ class TrainEngine:
         self.coef = cf[:S1]
 
     # ------------------------------------------------------------------ phases
-    def step(self, x, probs=None, eps=None, return_device=False):
+    def step(self, x, probs=None, eps=None, return_device=False, use_graph=False):
         """x: [T,B,C,H,W] fp32 on the device.  probs: host numpy uniform draws (None -> np.random.uniform,
         like models/p2p_model.py:215).  eps: [S,2,B,z] N(0,1) (None -> torch.randn on the device)."""
         T, B = int(x.shape[0]), int(x.shape[1])
@@ -223,8 +225,40 @@ class TrainEngine:
         self.T, self.B, self.S = T, B, plan.S
         if eps is None:
             eps = torch.randn(plan.S, 2, B, self.z, device=self.dev, dtype=torch.float32)
-        self.eps = eps.contiguous()
         self.upload_plan(plan)
+        if use_graph:
+            out = self._step_graphed(x, eps, plan)
+        else:
+            self.eps = eps.contiguous()
+            out = self._run(x, plan)
+        return out if return_device else out.cpu().numpy()
+
+    def _step_graphed(self, x, eps, plan):
+        """CUDA-graph replay of the whole step.  The first call with a new (T,B,S,...) signature runs eagerly
+        (allocating every buffer), the second captures, later ones only replay; index tables, counters and
+        inputs live in static device buffers that are refreshed before each replay."""
+        key = plan.key + (self.B,)
+        xs = self.fbuf("x_static", x.numel()).view(-1)[:x.numel()].view(x.shape)
+        es = self.fbuf("eps_static", eps.numel()).view(-1)[:eps.numel()].view(eps.shape)
+        xs.copy_(x, non_blocking=True)
+        es.copy_(eps, non_blocking=True)
+        self.eps = es
+        st = self._graphs.get(key)
+        if st is None:
+            self._graphs[key] = "warm"
+            return self._run(xs, plan)
+        if st == "warm":
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = self.K.launches
+            with torch.cuda.graph(g):
+                self._run(xs, plan)
+            self._graphs[key] = st = (g, self.K.launches - n0)
+        st[0].replay()
+        self.K.launches += st[1]
+        return self._bufs["loss_out"][:4]
+
+    def _run(self, x, plan):
         self.pack_weights()
         self.encode(x, plan)
         self.recurrent_fwd(plan)
@@ -239,8 +273,7 @@ class TrainEngine:
             self.backward_prior(plan)
             self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
         self.adam(("prior",))
-        out = self._bufs["loss_out"][:4]
-        return out if return_device else out.cpu().numpy()
+        return self._bufs["loss_out"][:4]
 
     # -- Phase E ----------------------------------------------------------------------------
     def encode(self, x, plan):
@@ -714,6 +747,13 @@ class TrainEngine:
     # -- optimiser --------------------------------------------------------------------------
     def adam(self, modules):
         opt = self.opt
+        if self.dist is not None:
+            # data parallel: replicas hold batch shards; average the flat gradient arenas over NVLink (NCCL)
+            dist, group, world = self.dist
+            for m in modules:
+                A = self.arena[m]
+                dist.all_reduce(A.grad, group=group)
+                self.K.scale(A.grad, A.numel, 1.0 / world)
         for m in modules:
             A = self.arena[m]
             A.step_t += 1

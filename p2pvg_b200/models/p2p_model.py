@@ -1,0 +1,192 @@
+"""``models.p2p_model.P2PModel`` drop-in (reference models/p2p_model.py:12-330): same constructor, attributes
+(``encoder``, ``decoder``, ``frame_predictor``, ``posterior``, ``prior``, ``*_optimizer``), ``forward`` return
+value, ``save`` / ``load`` checkpoint format — with ``forward`` executed by p2pvg_b200.engine.TrainEngine on
+hand-written sm_100a kernels.  ``train.py`` / ``generate.py`` of the reference run against it unchanged.
+
+Differences that are visible and documented: after ``forward`` the ``.grad`` of the four non-prior
+modules holds the gradient that was *applied* (backward #1); the reference additionally accumulates the
+never-applied backward #2 contribution there.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lstm as lstm_models
+from ..misc import criterion, utils
+
+MODULES = ("frame_predictor", "posterior", "prior", "encoder", "decoder")
+
+
+class ArenaAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam``-shaped handle (state_dict layout: step / exp_avg / exp_avg_sq per parameter) over one
+    module's flat parameter arena.  The update itself is the fused kernel p2pvg_adam_legacy, launched by the
+    engine inside the train step (PyTorch-1.0 arithmetic, which is what the reference pins)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps))
+        self._arena = None
+        self._names = None
+
+    def attach(self, arena, named_params):
+        self._arena = arena
+        for name, p in named_params:
+            m, v = arena.moment_views(name)
+            old = self.state.get(p, {})
+            if "exp_avg" in old:
+                m.copy_(old["exp_avg"])
+                v.copy_(old["exp_avg_sq"])
+                arena.step_t.fill_(int(old.get("step", 0)))
+            self.state[p] = dict(step=int(arena.step_t.item()), exp_avg=m, exp_avg_sq=v)
+
+    def sync_step(self):
+        if self._arena is not None:
+            t = int(self._arena.step_t.item())
+            for st in self.state.values():
+                st["step"] = t
+
+    def state_dict(self):
+        self.sync_step()
+        return super().state_dict()
+
+    def load_state_dict(self, sd):
+        arena = self._arena
+        super().load_state_dict(sd)
+        if arena is not None:  # re-home the loaded moments into the arena views
+            names = {id(p): n for n, p in self._named}
+            for p, st in list(self.state.items()):
+                m, v = arena.moment_views(names[id(p)])
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                arena.step_t.fill_(int(st["step"]))
+                self.state[p] = dict(step=int(st["step"]), exp_avg=m, exp_avg_sq=v)
+
+    def step(self, closure=None):
+        raise RuntimeError("ArenaAdam.step() is fused into P2PModel.forward (the reference also steps inside forward)")
+
+
+class P2PModel(nn.Module):
+    def __init__(self, batch_size=100, channels=1, g_dim=128, z_dim=10, rnn_size=256, prior_rnn_layers=1,
+                 posterior_rnn_layers=1, predictor_rnn_layers=2, opt=None):
+        super().__init__()
+        self.batch_size, self.channels, self.g_dim, self.z_dim, self.rnn_size = batch_size, channels, g_dim, z_dim, rnn_size
+        self.prior_rnn_layers, self.posterior_rnn_layers, self.predictor_rnn_layers = prior_rnn_layers, posterior_rnn_layers, predictor_rnn_layers
+        self.opt = opt
+        # construction order == reference (p2p_model.py:28-38) so the torch RNG stream matches
+        self.frame_predictor = lstm_models.lstm(g_dim + z_dim + 2, g_dim, rnn_size, predictor_rnn_layers, batch_size)
+        self.posterior = lstm_models.gaussian_lstm(2 * g_dim + 2, z_dim, rnn_size, posterior_rnn_layers, batch_size)
+        self.prior = lstm_models.gaussian_lstm(2 * g_dim + 2, z_dim, rnn_size, prior_rnn_layers, batch_size)
+        if getattr(opt, "dataset", None) == "h36m":
+            raise NotImplementedError("h36m_mlp backbone is not part of this build yet (SURVEY.md §8 row a8)")
+        self.encoder = opt.backbone_net.encoder(g_dim, channels)
+        self.decoder = opt.backbone_net.decoder(g_dim, channels)
+        opt.optimizer = ArenaAdam
+        self.mse_criterion = nn.MSELoss()
+        self.kl_criterion = criterion.KLCriterion(opt=opt)
+        self.align_criterion = nn.MSELoss()
+        self._engine = None
+        self.precision = os.environ.get("P2PVG_PRECISION", "bf16")
+        self.use_graph = os.environ.get("P2PVG_GRAPH", "1") != "0"
+        self.update_mode = os.environ.get("P2PVG_UPDATE_MODE", "A")
+        self.init_weight()
+        self.init_optimizer()
+
+    # ---- reference API -----------------------------------------------------------------------------
+    def init_optimizer(self):
+        opt = self.opt
+        for m in MODULES:
+            o = opt.optimizer(getattr(self, m).parameters(), lr=opt.lr, betas=(opt.beta1, 0.999))
+            o._named = list(getattr(self, m).named_parameters())
+            setattr(self, m + "_optimizer", o)
+        self._engine = None
+
+    def init_hidden(self, batch_size=1):
+        self.frame_predictor.hidden = self.frame_predictor.init_hidden(batch_size=batch_size)
+        self.posterior.hidden = self.posterior.init_hidden(batch_size=batch_size)
+        self.prior.hidden = self.prior.init_hidden(batch_size=batch_size)
+
+    def init_weight(self):
+        for m in MODULES:
+            getattr(self, m).apply(utils.init_weights)
+
+    def get_global_descriptor(self, x, start_ix=0, cp_ix=None):
+        if cp_ix is None:
+            cp_ix = len(x) - 1
+        x_cp = x[cp_ix]
+        return x_cp, self.encoder(x_cp)[0]
+
+    # ---- engine binding ----------------------------------------------------------------------------
+    def _opt_dict(self):
+        o = self.opt
+        return dict(beta=float(o.beta), weight_cpc=float(o.weight_cpc), weight_align=float(o.weight_align),
+                    skip_prob=float(o.skip_prob), n_past=int(o.n_past), last_frame_skip=bool(o.last_frame_skip),
+                    lr=float(o.lr), beta1=float(o.beta1), batch_size=int(o.batch_size))
+
+    def engine(self, width):
+        if self._engine is not None:
+            return self._engine
+        from .._lib import CudaKernels
+        from ..engine import TrainEngine
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("p2pvg_b200 has no CPU path: move the model to a CUDA device first (model.cuda())")
+        cfg = dict(g_dim=self.g_dim, z_dim=self.z_dim, rnn_size=self.rnn_size, channels=self.channels, image_width=width)
+        state = {m: getattr(self, m).state_dict() for m in MODULES}
+        adt = torch.float32 if self.precision == "fp32" else torch.bfloat16
+        eng = TrainEngine(state, cfg, self._opt_dict(), CudaKernels(dev), act_dtype=adt, mode=self.update_mode)
+        for m in MODULES:
+            mod = getattr(self, m)
+            named = list(mod.named_parameters())
+            for k, p in named:  # parameters become views of the flat arena; .grad views of the grad arena
+                p.data = eng.arena[m].p[k]
+                p.grad = eng.arena[m].g[k]
+            for k in list(eng.buffers[m].keys()):
+                owner, _, leaf = k.rpartition(".")
+                mod.get_submodule(owner)._buffers[leaf] = eng.buffers[m][k]
+            getattr(self, m + "_optimizer").attach(eng.arena[m], named)
+        self._engine = eng
+        return eng
+
+    def forward(self, x, start_ix=0, cp_ix=-1):
+        """One training step; returns (mse, kld, cpc, align) numpy scalars divided by seq_len
+        (reference models/p2p_model.py:185-271)."""
+        if isinstance(x, tuple):
+            raise NotImplementedError("h36m tuple input is not part of this build yet")
+        if not torch.is_tensor(x):
+            x = torch.stack(list(x))
+        eng = self.engine(int(x.shape[-1]))
+        eng.opt = self._opt_dict()
+        out = eng.step(x.float(), use_graph=self.use_graph, return_device=True)
+        host = out.cpu().numpy()
+        for m in MODULES:  # model.zero_grad() drops .grad; keep them readable for train.py's histograms
+            for k, p in getattr(self, m).named_parameters():
+                p.grad = eng.arena[m].g[k]
+        return host[0], host[1], host[2], host[3]
+
+    def p2p_generate(self, x, len_output, eval_cp_ix, start_ix=0, cp_ix=-1, model_mode='full', skip_frame=False,
+                     init_hidden=True):
+        from ..infer import p2p_generate
+        return p2p_generate(self, x, len_output, eval_cp_ix, model_mode=model_mode, skip_frame=skip_frame, init_hidden=init_hidden)
+
+    # ---- checkpoints (same dict layout as reference p2p_model.py:289-330) --------------------------
+    def save(self, fname, epoch):
+        backbone_net, optimizer = self.opt.backbone_net, getattr(self.opt, "optimizer", None)
+        self.opt.backbone_net, self.opt.optimizer = 0, 0
+        states = {m: getattr(self, m).state_dict() for m in MODULES}
+        states.update({m + "_opt": getattr(self, m + "_optimizer").state_dict() for m in MODULES})
+        states.update(epoch=epoch, opt=self.opt)
+        torch.save(states, fname)
+        self.opt.backbone_net, self.opt.optimizer = backbone_net, optimizer
+
+    def load(self, pth=None, states=None):
+        if states is None:
+            states = torch.load(pth, weights_only=False)
+        for m in MODULES:
+            getattr(self, m).load_state_dict(states[m])
+            getattr(self, m + "_optimizer").load_state_dict(states[m + "_opt"])
+        keep = (self.opt.backbone_net, getattr(self.opt, "optimizer", None))
+        self.opt = states["opt"]
+        self.opt.backbone_net, self.opt.optimizer = keep
+        return states["epoch"] + 1

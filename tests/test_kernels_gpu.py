@@ -65,7 +65,7 @@ TC_SHAPES = [
     (128, 64, 64, False, False), (70, 16, 128, False, False), (1000, 48, 72, False, False),
     (256, 128, 128, False, True), (192, 4096, 128, False, True), (130, 16, 128, False, True),
     (128, 128, 128, True, True), (64, 1024, 4096, True, True), (512, 136, 1000, True, True), (128, 16, 3000, True, True),
-    (256, 128, 64, True, False), (100, 72, 200, True, False),
+    (256, 128, 64, True, False), (104, 72, 200, True, False),
     (128, 128, 16, False, False), (2048, 64, 16, False, False), (64, 1024, 100000, True, True),
 ]
 

