@@ -84,6 +84,16 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def host_threads():
+    """Threads for the CPU reference: the reference path is ~93k small ATen ops per step; beyond
+    a few dozen threads the per-op fork/join cost dominates, so cap at 32 (P2PVG_CPU_THREADS overrides)."""
+    return int(os.environ.get("P2PVG_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+
+
 def make_opt(backbone, batch):
     return types.SimpleNamespace(dataset="mnist", backbone_net=backbone, lr=1e-3, beta1=0.9, beta=1e-4, weight_cpc=100.0,
                                  weight_align=0.5, skip_prob=0.0, n_past=1, last_frame_skip=False, batch_size=batch)
@@ -105,6 +115,7 @@ def cpu_reference_steps(T, B, steps, warmup, threads):
         t0 = time.perf_counter()
         O.train_step(state, adam, x, opt, 64, eps, probs, mode="A")
         dt = time.perf_counter() - t0
+        log(f'cpu reference step {it}: {dt:.2f} s')
         if it >= warmup:
             times.append(dt)
     return times
@@ -115,7 +126,7 @@ def run_reference(args):
     if rank != 0:
         return
     T, B = args.seq, args.ref_batch
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     times = cpu_reference_steps(T, B, args.steps, args.warmup, threads)
     tot = sum(times)
     val = T * B * len(times) / tot
@@ -177,6 +188,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('model built; warm-up')
     # ---- device-timed, batch resident in HBM --------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         eng.step(x_dev, use_graph=use_graph, return_device=True)
@@ -196,6 +208,7 @@ def main():
     barrier()
     tw1 = time.time()
     launches = K.launches - n0
+    log(f'timed region done: {e0.elapsed_time(e1) / args.steps:.2f} ms/step')
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -217,6 +230,7 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_val = T * B * world / (ms2.item() / args.steps * 1e-3)
 
+    log(f'e2e done: {ms2.item() / args.steps:.2f} ms/step')
     # ---- roofline of the dominant kernel: instrumented eager pass ----------------------------------
     roof = None
     if rank == 0 and args.precision == "bf16":
@@ -249,8 +263,10 @@ def main():
     # ---- CPU baseline (oracle port) on the host cores: bounded sample -------------------------------
     cpu = None
     if rank == 0 and not args.skip_cpu:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
+        log(f'cpu baseline on {threads} threads')
         times = cpu_reference_steps(T, args.ref_batch, 2, 1, threads)
+        log(f'cpu baseline done: {times}')
         cpu = dict(value=T * args.ref_batch * len(times) / sum(times), unit="frames/s", cores=threads, kind="port",
                    sample=f"2 steps of T={T},B={args.ref_batch} (config C1 shape) of the oracle port, all host threads")
 

@@ -103,7 +103,8 @@ int p2pvg_gather_add_cols(float* dst, const float* src, const int* idx, int S, i
 int p2pvg_align(const float* H, const int* in_idx, const float* h_pred, int P, int B, int g, float coef, float* loss_partial,
                 float* d_hpred, float* dH, void* stream);
 /* out[c] (+)= sum_r x[r*ld + c] — bias gradients. */
-int p2pvg_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* out, int accumulate, void* stream);
+int p2pvg_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* out, int accumulate, void* ws /* >= 1024*cols floats */,
+                 size_t ws_bytes, void* stream);
 int p2pvg_act_fwd(float* x, int64_t n, int act, void* stream);
 int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
 

@@ -182,7 +182,9 @@ class CudaKernels:
                                       _p(dH), self._stream()))
 
     def colsum(self, x, rows, cols, ld, out, accumulate=False):
-        self._ck(self.lib.p2pvg_colsum(_p(x), _i(_dt(x)), _i64(rows), _i(cols), _i64(ld), _p(out), _i(int(accumulate)), self._stream()))
+        ws = self.bn_workspace(1, 1)
+        self._ck(self.lib.p2pvg_colsum(_p(x), _i(_dt(x)), _i64(rows), _i(cols), _i64(ld), _p(out), _i(int(accumulate)), _p(ws),
+                                       _sz(ws.numel()), self._stream()))
 
     def act_fwd(self, x, n, act):
         self._ck(self.lib.p2pvg_act_fwd(_p(x), _i64(n), _i(act), self._stream()))

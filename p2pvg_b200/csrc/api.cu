@@ -55,7 +55,7 @@ int p2pvg_build_concat_impl(float*, const float*, const int*, int, const float*,
                             cudaStream_t);
 int p2pvg_gather_add_cols_impl(float*, const float*, const int*, int, int, int, int, int, int, int, cudaStream_t);
 int p2pvg_align_impl(const float*, const int*, const float*, int, int, int, float, float*, float*, float*, cudaStream_t);
-int p2pvg_colsum_impl(const void*, int, long long, int, long long, float*, int, cudaStream_t);
+int p2pvg_colsum_impl(const void*, int, long long, int, long long, float*, int, void*, size_t, cudaStream_t);
 int p2pvg_act_fwd_impl(float*, long long, int, cudaStream_t);
 int p2pvg_act_bwd_impl(const float*, const float*, float*, long long, int, cudaStream_t);
 int p2pvg_mse_chunks_impl();
@@ -160,8 +160,9 @@ int p2pvg_align(const float* H, const int* in_idx, const float* h_pred, int P, i
                 float* d_hpred, float* dH, void* stream) {
   return p2pvg_align_impl(H, in_idx, h_pred, P, B, g, coef, loss_partial, d_hpred, dH, ST);
 }
-int p2pvg_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* out, int accumulate, void* stream) {
-  return p2pvg_colsum_impl(x, dtype, rows, cols, ld, out, accumulate, ST);
+int p2pvg_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* out, int accumulate, void* ws, size_t ws_bytes,
+                 void* stream) {
+  return p2pvg_colsum_impl(x, dtype, rows, cols, ld, out, accumulate, ws, ws_bytes, ST);
 }
 int p2pvg_act_fwd(float* x, int64_t n, int act, void* stream) { return p2pvg_act_fwd_impl(x, n, act, ST); }
 int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream) {

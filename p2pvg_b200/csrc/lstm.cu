@@ -157,15 +157,18 @@ __global__ void align_kernel(const float* __restrict__ H, const int* __restrict_
   }
 }
 
-// out[c] (+)= sum_r x[r, c]
+// out[c] (+)= sum_r x[r, c]   — two deterministic stages: per-chunk partials, then a column-wise finish
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ out,
-                              int accumulate) {
+__global__ void colsum_partial_kernel(const T* __restrict__ x, long long rows, int cols, long long ld, long long rows_per_chunk,
+                                      float* __restrict__ part) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int lane = threadIdx.x >> 5;  // 8 row lanes
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
   float acc = 0.f;
   if (c < cols)
-    for (long long r = lane; r < rows; r += 8) acc += ld_f<T>(&x[r * ld + c]);
+    for (long long r = r0 + lane; r < r1; r += 8) acc += ld_f<T>(&x[r * ld + c]);
   __shared__ float sh[8][33];
   sh[lane][threadIdx.x & 31] = acc;
   __syncthreads();
@@ -173,8 +176,15 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int cols,
     float v = 0.f;
 #pragma unroll
     for (int l = 0; l < 8; l++) v += sh[l][threadIdx.x & 31];
-    out[c] = accumulate ? out[c] + v : v;
+    part[(long long)blockIdx.y * cols + c] = v;
   }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int nchunk, int cols, float* __restrict__ out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float v = 0.f;
+  for (int k = 0; k < nchunk; k++) v += part[(long long)k * cols + c];
+  out[c] = accumulate ? out[c] + v : v;
 }
 
 __global__ void act_fwd_kernel(float* __restrict__ x, long long n, int act) {
@@ -245,9 +255,22 @@ int p2pvg_align_impl(const float* H, const int* in_idx, const float* h_pred, int
   align_kernel<<<P, 128, 0, st>>>(H, in_idx, h_pred, P, B, g, coef, loss_partial, d_hpred, dH);
   return p2pvg_check_launch("align");
 }
-int p2pvg_colsum_impl(const void* x, int dtype, long long rows, int cols, long long ld, float* out, int accumulate, cudaStream_t st) {
+int p2pvg_colsum_impl(const void* x, int dtype, long long rows, int cols, long long ld, float* out, int accumulate, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
   if (cols == 0) return P2PVG_OK;
-  DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<cdiv(cols, 32), 256, 0, st>>>((const T*)x, rows, cols, ld, out, accumulate)));
+  // enough chunks to fill the machine (148 SMs x a few blocks), at least 64 rows per chunk
+  long long want = (148LL * 8) / cdiv(cols, 32) + 1;
+  long long maxc = (rows + 63) / 64;
+  long long nchunk = want < maxc ? want : maxc;
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 1024) nchunk = 1024;
+  P2PVG_REQUIRE(ws != nullptr && ws_bytes >= (size_t)nchunk * cols * sizeof(float), P2PVG_ERR_WORKSPACE, "colsum: workspace too small");
+  long long rpc = (rows + nchunk - 1) / nchunk;
+  if (rpc < 1) rpc = 1;
+  nchunk = rows > 0 ? (rows + rpc - 1) / rpc : 1;
+  dim3 grid(cdiv(cols, 32), (unsigned)nchunk);
+  DISPATCH_DTYPE(dtype, T, (colsum_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, rows, cols, ld, rpc, (float*)ws)));
+  colsum_finish_kernel<<<cdiv(cols, 128), 128, 0, st>>>((const float*)ws, (int)nchunk, cols, out, accumulate);
   return p2pvg_check_launch("colsum");
 }
 int p2pvg_act_fwd_impl(float* x, long long n, int act, cudaStream_t st) {
