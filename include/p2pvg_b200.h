@@ -42,6 +42,9 @@ const char* p2pvg_last_error(void);
 int p2pvg_has_tcgen05(void);
 /* 0 = pick automatically (tcgen05 for bf16 operands), 1 = force the CUDA-core GEMM, 2 = force tcgen05 */
 int p2pvg_set_gemm_impl(int impl);
+/* fp32-operand GEMMs: 0 = exact fp32 on the CUDA cores (parity mode), 1 = tcgen05 kind::tf32 when both operands are
+ * K-major and TMA-compatible (used for the LSTM GEMMs of the bf16 training mode). */
+int p2pvg_set_fp32_gemm_mode(int mode);
 
 /* C[M,N] = (accumulate ? C : 0) + opA(A)*opB(B) + bias[n] + addend[m,n]
  *   a_mn=0: A[m*lda+k] (K-major), a_mn=1: A[k*lda+m];  b_mn=0: B[n*ldb+k], b_mn=1: B[k*ldb+n].
@@ -96,7 +99,7 @@ int p2pvg_reparam_kl_bwd(const float* mu, const float* lv, const float* mu_p, co
                          float* dmu_p, float* dlv_p, int n, void* stream);
 /* torch.cat([h, global_z | z, time_until_cp, delta_time], 1) (models/p2p_model.py:241-242,247,252) for all steps. */
 int p2pvg_build_concat(float* dst, const float* A, const int* ia, int ga, const float* Bm, const int* ib, int gb,
-                       const float* tuc, const float* dt, int S, int B, void* stream);
+                       const float* tuc, const float* dt, int S, int B, int ld /* row pitch >= ga+gb+2, zero padded */, void* stream);
 int p2pvg_gather_add_cols(float* dst, const float* src, const int* idx, int S, int T, int B, int g, int W, int col0, int init,
                           void* stream);
 /* align_loss += MSE(h[0], h_pred) with h[0] = batch row 0 broadcast (models/p2p_model.py:224-225), value + gradients. */

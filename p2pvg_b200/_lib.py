@@ -96,6 +96,12 @@ class CudaKernels:
         self._ck(self.lib.p2pvg_set_gemm_impl(_i({"auto": 0, "simt": 1, "tc": 2}[impl])))
         self.launches -= 1
 
+    def set_fp32_gemm_mode(self, mode: int):
+        """0: fp32 GEMMs exact on the CUDA cores; 1: K-major fp32 GEMMs on the tensor cores at TF32 precision."""
+        rc = self.lib.p2pvg_set_fp32_gemm_mode(_i(mode))
+        if rc != 0:
+            raise KernelError("set_fp32_gemm_mode failed")
+
     def has_tcgen05(self) -> bool:
         return bool(self.lib.p2pvg_has_tcgen05())
 
@@ -107,7 +113,7 @@ class CudaKernels:
         ldc = ldc if ldc is not None else N
         ldd = ldd if ldd is not None else N
         assert A.dtype == B.dtype
-        ws = self.gemm_workspace() if A.dtype == torch.bfloat16 else None
+        ws = self.gemm_workspace()
         self._ck(self.lib.p2pvg_gemm(_p(A), _i(_dt(A)), _i(int(a_mn)), _i64(lda), _p(B), _i(int(b_mn)), _i64(ldb), _p(C),
                                      _i(_dt(C)), _i64(ldc), _i(M), _i(N), _i(K), _i(int(accumulate)), _p(bias), _p(addend),
                                      _i64(ldd), _p(ws), _sz(ws.numel() if ws is not None else 0), self._stream()))
@@ -169,9 +175,9 @@ class CudaKernels:
         self._ck(self.lib.p2pvg_reparam_kl_bwd(_p(mu), _p(lv), _p(mu_p), _p(lv_p), _p(eps), _p(eps_p), _p(dz), _p(dz_p),
                                                _f(kl_coef), _p(dmu), _p(dlv), _p(dmu_p), _p(dlv_p), _i(n), self._stream()))
 
-    def build_concat(self, dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B):
+    def build_concat(self, dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B, ld=None):
         self._ck(self.lib.p2pvg_build_concat(_p(dst), _p(A), _p(ia), _i(ga), _p(Bm), _p(ib), _i(gb), _p(tuc), _p(dt), _i(S), _i(B),
-                                             self._stream()))
+                                             _i(ld if ld is not None else ga + gb + 2), self._stream()))
 
     def gather_add_cols(self, dst, src, idx, S, T, B, g, W, col0, init=False):
         self._ck(self.lib.p2pvg_gather_add_cols(_p(dst), _p(src), _p(idx), _i(S), _i(T), _i(B), _i(g), _i(W), _i(col0),

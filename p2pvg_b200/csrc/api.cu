@@ -27,7 +27,9 @@ int p2pvg_check_launch(const char* what) {
 
 // ---- implemented in the other translation units ----
 int p2pvg_gemm_simt(const void*, int, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int,
-                    const float*, const void*, long long, cudaStream_t);
+                    const float*, const void*, long long, void*, size_t, cudaStream_t);
+int p2pvg_gemm_tf32(const void*, long long, const void*, long long, void*, int, long long, int, int, int, int, const float*,
+                    const void*, long long, cudaStream_t);
 int p2pvg_gemm_tc(const void*, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int, const float*,
                   const void*, long long, void*, size_t, cudaStream_t);
 int p2pvg_gemm_tc_available();
@@ -52,7 +54,7 @@ int p2pvg_reparam_kl_fwd_impl(const float*, const float*, const float*, const fl
 int p2pvg_reparam_kl_bwd_impl(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
                               const float*, float, float*, float*, float*, float*, int, cudaStream_t);
 int p2pvg_build_concat_impl(float*, const float*, const int*, int, const float*, const int*, int, const float*, const float*, int, int,
-                            cudaStream_t);
+                            int, cudaStream_t);
 int p2pvg_gather_add_cols_impl(float*, const float*, const int*, int, int, int, int, int, int, int, cudaStream_t);
 int p2pvg_align_impl(const float*, const int*, const float*, int, int, int, float, float*, float*, float*, cudaStream_t);
 int p2pvg_colsum_impl(const void*, int, long long, int, long long, float*, int, void*, size_t, cudaStream_t);
@@ -66,6 +68,7 @@ int p2pvg_scale_impl(float*, long long, float, cudaStream_t);
 
 static int g_gemm_impl = 0;  // 0 auto, 1 simt, 2 tcgen05
 int p2pvg_gemm_impl_forced() { return g_gemm_impl; }
+static int g_fp32_mode = 0;  // 0 exact fp32 on CUDA cores, 1 TF32 tensor cores for K-major fp32 operands
 
 #define ST ((cudaStream_t)stream)
 
@@ -80,6 +83,12 @@ int p2pvg_set_gemm_impl(int impl) {
   return P2PVG_OK;
 }
 
+int p2pvg_set_fp32_gemm_mode(int mode) {
+  if (mode < 0 || mode > 1) return P2PVG_ERR_BAD_ARG;
+  g_fp32_mode = mode;
+  return P2PVG_OK;
+}
+
 int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int c_dtype,
                int64_t ldc, int M, int N, int K, int accumulate, const float* bias, const void* addend, int64_t ldd,
                void* workspace, size_t ws_bytes, void* stream) {
@@ -90,7 +99,12 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
   // refuse to fall back when an operand is not TMA-compatible.
   if (want_tc)
     return p2pvg_gemm_tc(A, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace, ws_bytes, ST);
-  return p2pvg_gemm_simt(A, in_dtype, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, ST);
+  if (in_dtype == P2PVG_F32 && g_fp32_mode == 1 && g_gemm_impl != 1 && !a_mn && !b_mn && K >= 32) {
+    int rc = p2pvg_gemm_tf32(A, lda, B, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, ST);
+    if (rc != P2PVG_ERR_UNSUPPORTED) return rc;  // not TMA-compatible -> CUDA-core kernel below
+  }
+  return p2pvg_gemm_simt(A, in_dtype, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace,
+                         ws_bytes, ST);
 }
 
 int p2pvg_im2col_k4s2p1(const void* x, void* col, int dtype, int N, int H, int W, int C, void* stream) {
@@ -149,8 +163,8 @@ int p2pvg_reparam_kl_bwd(const float* mu, const float* lv, const float* mu_p, co
   return p2pvg_reparam_kl_bwd_impl(mu, lv, mu_p, lv_p, eps, eps_p, dz, dz_p, kl_coef, dmu, dlv, dmu_p, dlv_p, n, ST);
 }
 int p2pvg_build_concat(float* dst, const float* A, const int* ia, int ga, const float* Bm, const int* ib, int gb,
-                       const float* tuc, const float* dt, int S, int B, void* stream) {
-  return p2pvg_build_concat_impl(dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B, ST);
+                       const float* tuc, const float* dt, int S, int B, int ld, void* stream) {
+  return p2pvg_build_concat_impl(dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B, ld, ST);
 }
 int p2pvg_gather_add_cols(float* dst, const float* src, const int* idx, int S, int T, int B, int g, int W, int col0, int init,
                           void* stream) {

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
                                                         const TI* __restrict__ B, int b_mn, long long ldb,
                                                         TO* __restrict__ C, long long ldc, int M, int N, int K,
                                                         int accumulate, const float* __restrict__ bias,
-                                                        const TO* __restrict__ addend, long long ldd) {
+                                                        const TO* __restrict__ addend, long long ldd,
+                                                        float* __restrict__ partial, int k_per_split) {
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -29,7 +30,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  K = kend;  // loads beyond this split's range read as zero
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
     // ---- stage A tile (BM x BK) ----
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -76,6 +80,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
       int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = acc[i][j];
+      if (partial) {  // split-K: raw partial sums, finished by simt_splitk_reduce_kernel
+        partial[((long long)blockIdx.z * M + gm) * N + gn] = v;
+        continue;
+      }
       if (bias) v += bias[gn];
       if (addend) v += ld_f<TO>(&addend[gm * ldd + gn]);
       if (accumulate) v += ld_f<TO>(&C[gm * ldc + gn]);
@@ -84,17 +92,47 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
   }
 }
 
+template <typename TO>
+__global__ void simt_splitk_reduce_kernel(const float* __restrict__ partial, int splits, TO* __restrict__ C, long long ldc, int M, int N,
+                                          int accumulate, const float* __restrict__ bias, const TO* __restrict__ addend, long long ldd) {
+  const long long total = (long long)M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / N;
+    const int n = (int)(idx - m * N);
+    float acc = 0.f;
+    for (int z = 0; z < splits; z++) acc += partial[(long long)z * total + idx];
+    if (bias) acc += bias[n];
+    if (addend) acc += ld_f<TO>(&addend[m * ldd + n]);
+    if (accumulate) acc += ld_f<TO>(&C[m * ldc + n]);
+    st_f<TO>(&C[m * ldc + n], acc);
+  }
+}
+
 }  // namespace
 
 int p2pvg_gemm_simt(const void* A, int in_dtype, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* C,
                     int c_dtype, long long ldc, int M, int N, int K, int accumulate, const float* bias,
-                    const void* addend, long long ldd, cudaStream_t stream) {
+                    const void* addend, long long ldd, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return P2PVG_OK;
   dim3 grid(cdiv(M, BM), cdiv(N, BN));
+  // split-K (deterministic two-pass) for small outputs with a long reduction, e.g. the Linear weight gradients
+  int splits = 1, k_per_split = K > 0 ? K : 1;
+  const long long tiles = (long long)grid.x * grid.y;
+  if (tiles < 74 && K >= 2048 && workspace != nullptr) {
+    long long want = (296 + tiles - 1) / tiles;
+    long long maxs = K / 256;
+    splits = (int)(want < maxs ? want : maxs);
+    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) splits /= 2;
+    if (splits < 1) splits = 1;
+    k_per_split = ((cdiv(K, splits) + BK - 1) / BK) * BK;
+    splits = cdiv(K, k_per_split);
+  }
+  grid.z = splits;
+  float* partial = splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
   P2PVG_REQUIRE(grid.y <= 65535, P2PVG_ERR_UNSUPPORTED, "gemm_simt: N=%d too large", N);
 #define LAUNCH(TI, TO)                                                                                              \
   gemm_simt_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)A, a_mn, lda, (const TI*)B, b_mn, ldb, (TO*)C, ldc, \
-                                                     M, N, K, accumulate, bias, (const TO*)addend, ldd)
+                                                     M, N, K, accumulate, bias, (const TO*)addend, ldd, partial, k_per_split)
   if (in_dtype == P2PVG_F32 && c_dtype == P2PVG_F32) LAUNCH(float, float);
   else if (in_dtype == P2PVG_BF16 && c_dtype == P2PVG_F32) LAUNCH(bf16, float);
   else if (in_dtype == P2PVG_BF16 && c_dtype == P2PVG_BF16) LAUNCH(bf16, bf16);
@@ -104,5 +142,13 @@ int p2pvg_gemm_simt(const void* A, int in_dtype, int a_mn, long long lda, const 
     return P2PVG_ERR_BAD_ARG;
   }
 #undef LAUNCH
+  if (splits > 1) {
+    long long total = (long long)M * N;
+    int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+    if (c_dtype == P2PVG_BF16)
+      simt_splitk_reduce_kernel<bf16><<<blocks, 256, 0, stream>>>(partial, splits, (bf16*)C, ldc, M, N, accumulate, bias, (const bf16*)addend, ldd);
+    else
+      simt_splitk_reduce_kernel<float><<<blocks, 256, 0, stream>>>(partial, splits, (float*)C, ldc, M, N, accumulate, bias, (const float*)addend, ldd);
+  }
   return p2pvg_check_launch("gemm_simt");
 }

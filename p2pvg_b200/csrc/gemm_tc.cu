@@ -20,13 +20,12 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
-constexpr int UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int ROW_BYTES = 128;  // one SWIZZLE_128B row: 64 bf16 or 32 fp32 (tf32) along the contiguous dimension
+constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
 constexpr int NUM_THREADS = 192;
 
 template <int BN> struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_STAGE_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 128) ? 6 : 8;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -74,6 +73,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -102,12 +111,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, bool A_MN, bool B_MN>
+template <typename TIn, int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv,
                int c_bf16, long long ldc, int M, int N, int K, int accumulate, const float* __restrict__ bias,
                const void* __restrict__ addend, long long ldd, float* __restrict__ partial, int kb_per_split) {
   using C_ = Cfg<BN>;
+  constexpr int ELEM = sizeof(TIn);
+  constexpr int BLOCK_K = ROW_BYTES / ELEM;  // elements of K per pipeline stage (K-major) / rows per stage (MN-major)
+  constexpr int UMMA_K = 32 / ELEM;          // K per tcgen05.mma: 16 for bf16, 8 for tf32
+  constexpr bool TF32 = (ELEM == 4);
+  static_assert(!(TF32 && (A_MN || B_MN)), "tf32 path supports K-major operands only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
@@ -169,7 +183,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      const uint32_t fmt = TF32 ? 2u : 1u;  // operand format: 1 = bf16, 2 = tf32
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       for (int i = 0; i < nkb; i++) {
         const int s = i % C_::STAGES;
@@ -181,9 +196,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
           // K-major: 16 bf16 = 32 B further inside the 128 B swizzle row; MN-major: 16 rows of 128 B further
-          const uint64_t da = A_MN ? make_desc(sa + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sa + k * UMMA_K * 2, 0, 1024);
-          const uint64_t db = B_MN ? make_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sb + k * UMMA_K * 2, 0, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          const uint64_t da = A_MN ? make_desc(sa + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sa + k * 32, 0, 1024);
+          const uint64_t db = B_MN ? make_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sb + k * 32, 0, 1024);
+          if (TF32) umma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          else umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
       }
@@ -308,7 +324,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
-int g_attr_done[2][2][2] = {};
+int g_attr_done[2][2][2][2] = {};
 
 void resolve_driver() {
   void* fn = nullptr;
@@ -319,12 +335,12 @@ void resolve_driver() {
 }
 
 // 2-D bf16 tensor map: dim0 (contiguous) x dim1, row pitch ld elements, box (64 x box1), 128B swizzle, zero OOB fill
-int make_map(CUtensorMap* map, const void* base, long long dim0, long long dim1, long long ld, int box1) {
+int make_map(CUtensorMap* map, const void* base, long long dim0, long long dim1, long long ld, int box1, int elem = 2) {
   cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem), (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -334,11 +350,11 @@ int make_map(CUtensorMap* map, const void* base, long long dim0, long long dim1,
   return P2PVG_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <typename TIn, int BN, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, int M, int N, int K, int accumulate,
            const float* bias, const void* addend, long long ldd, float* partial, int splits, int kb_per_split, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
-  int& done = g_attr_done[BN == 128][A_MN][B_MN];
+  auto kern = gemm_tc_kernel<TIn, BN, A_MN, B_MN>;
+  int& done = g_attr_done[sizeof(TIn) == 4][BN == 128][A_MN][B_MN];
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -361,9 +377,28 @@ int p2pvg_gemm_tc_available() {
 }
 
 int p2pvg_gemm_simt(const void*, int, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int,
-                    const float*, const void*, long long, cudaStream_t);
+                    const float*, const void*, long long, void*, size_t, cudaStream_t);
 
-static bool tc_operand_ok(const void* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 8 == 0); }
+static bool tc_operand_ok(const void* p, long long ld, int elem = 2) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld * elem) % 16 == 0);
+}
+
+// fp32 operands on the tensor cores at TF32 precision (K-major operands only).  Returns P2PVG_ERR_UNSUPPORTED when the
+// operands are not TMA-compatible so that the caller can use the CUDA-core kernel instead.
+int p2pvg_gemm_tf32(const void* A, long long lda, const void* B, long long ldb, void* C, int c_dtype, long long ldc, int M, int N,
+                    int K, int accumulate, const float* bias, const void* addend, long long ldd, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return P2PVG_OK;
+  if (!p2pvg_gemm_tc_available() || !tc_operand_ok(A, lda, 4) || !tc_operand_ok(B, ldb, 4) || K <= 0) return P2PVG_ERR_UNSUPPORTED;
+  const int BN = (N > 64) ? 128 : 64;
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, A, K, M, lda, BLOCK_M, 4);
+  if (rc) return rc;
+  rc = make_map(&tb, B, K, N, ldb, BN, 4);
+  if (rc) return rc;
+  const int nkb = cdiv(K, 32);
+  if (BN == 128) return launch<float, 128, false, false>(ta, tb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, nullptr, 1, nkb, st);
+  return launch<float, 64, false, false>(ta, tb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, nullptr, 1, nkb, st);
+}
 
 int p2pvg_gemm_tc(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* C, int c_dtype, long long ldc,
                   int M, int N, int K, int accumulate, const float* bias, const void* addend, long long ldd, void* workspace,
@@ -376,11 +411,12 @@ int p2pvg_gemm_tc(const void* A, int a_mn, long long lda, const void* B, int b_m
                       p2pvg_gemm_tc_available());
       return P2PVG_ERR_UNSUPPORTED;
     }
-    return p2pvg_gemm_simt(A, P2PVG_BF16, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, st);
+    return p2pvg_gemm_simt(A, P2PVG_BF16, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace, ws_bytes, st);
   }
   const int BN = (N > 64) ? 128 : 64;
   CUtensorMap ta, tb;
   int rc;
+  constexpr int BLOCK_K = 64;
   if (a_mn) rc = make_map(&ta, A, M, K, lda, BLOCK_K);
   else rc = make_map(&ta, A, K, M, lda, BLOCK_M);
   if (rc) return rc;
@@ -408,7 +444,7 @@ int p2pvg_gemm_tc(const void* A, int a_mn, long long lda, const void* B, int b_m
   float* partial = splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
 
 #define GO(BN_, AM, BM)                                                                                                     \
-  rc = launch<BN_, AM, BM>(ta, tb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, partial, splits, kb_per_split, st)
+  rc = launch<bf16, BN_, AM, BM>(ta, tb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, partial, splits, kb_per_split, st)
   if (BN == 128) {
     if (a_mn && b_mn) GO(128, true, true);
     else if (a_mn) GO(128, true, false);

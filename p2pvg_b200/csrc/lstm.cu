@@ -95,8 +95,8 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float*
 // dst[s,b,:] = [ A[ia[s],b,0:ga] | Bm[ib[s],b,0:gb] | tuc[s] | dt[s] ]
 __global__ void build_concat_kernel(float* __restrict__ dst, const float* __restrict__ A, const int* __restrict__ ia, int ga,
                                     const float* __restrict__ Bm, const int* __restrict__ ib, int gb, const float* __restrict__ tuc,
-                                    const float* __restrict__ dt, int S, int B) {
-  const int W = ga + gb + 2;
+                                    const float* __restrict__ dt, int S, int B, int W) {
+  // W >= ga+gb+2 is the row pitch; the padding columns are written as zeros
   long long total = (long long)S * B * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     int col = (int)(idx % W);
@@ -106,7 +106,8 @@ __global__ void build_concat_kernel(float* __restrict__ dst, const float* __rest
     if (col < ga) v = A[((long long)ia[s] * B + b) * ga + col];
     else if (col < ga + gb) v = Bm[((long long)ib[s] * B + b) * gb + (col - ga)];
     else if (col == ga + gb) v = tuc[s];
-    else v = dt[s];
+    else if (col == ga + gb + 1) v = dt[s];
+    else v = 0.f;
     dst[idx] = v;
   }
 }
@@ -236,10 +237,11 @@ int p2pvg_reparam_kl_bwd_impl(const float* mu, const float* lv, const float* mu_
   return p2pvg_check_launch("reparam_kl_bwd");
 }
 int p2pvg_build_concat_impl(float* dst, const float* A, const int* ia, int ga, const float* Bm, const int* ib, int gb,
-                            const float* tuc, const float* dt, int S, int B, cudaStream_t st) {
-  long long total = (long long)S * B * (ga + gb + 2);
+                            const float* tuc, const float* dt, int S, int B, int ld, cudaStream_t st) {
+  P2PVG_REQUIRE(ld >= ga + gb + 2, P2PVG_ERR_BAD_ARG, "build_concat: row pitch %d < %d", ld, ga + gb + 2);
+  long long total = (long long)S * B * ld;
   if (total == 0) return P2PVG_OK;
-  build_concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B);
+  build_concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B, ld);
   return p2pvg_check_launch("build_concat");
 }
 int p2pvg_gather_add_cols_impl(float* dst, const float* src, const int* idx, int S, int T, int B, int g, int W, int col0, int init,

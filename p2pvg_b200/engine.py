@@ -142,6 +142,8 @@ class TrainEngine:
         self._packed = {}
         self._graphs = {}
         self.dist = None  # (torch.distributed, group, world_size) when batch-sharded over several GPUs
+        # bf16 mode: the fp32 LSTM GEMMs run on the tensor cores at TF32 precision; fp32 mode stays exact
+        self.tc_lstm = (act_dtype == torch.bfloat16) and hasattr(kernels, "set_fp32_gemm_mode")
         self.last_plan = None
 
     # ------------------------------------------------------------------ memory
@@ -195,6 +197,51 @@ class TrainEngine:
                     b16 = self.fbuf("bias16_upc1", 16 * co)
                     K.permute4(P[cn + ".bias"], b16, (16, co, 1, 1), (0, 1, 0, 0))
                     self._packed["dec-1.bias16"] = b16
+
+    def pack_lstm_weights(self):
+        """Tensor-core (TF32) mode only: K-major fp32 copies of the LSTM weights for the GEMMs whose natural
+        operand layout is MN-major (data gradients), and a zero-padded embed weight so that the row pitch of
+        the 258 / 140-wide inputs is TMA-compatible."""
+        if not self.tc_lstm:
+            return
+        K = self.K
+        for m in ("frame_predictor", "posterior", "prior"):
+            P = self.arena[m].p
+            R = self.R
+            w = P["embed.weight"]
+            in_dim = w.shape[1]
+            in_p = (in_dim + 7) // 8 * 8
+            # re-pitch [R,in_dim] -> [R,in_p]: columns >= in_dim pick up the first elements of the next row
+            # (finite weights); they only ever multiply the zero padding columns of the input, so the product is exact
+            wp = self.fbuf(f"{m}_embed_pad", R * in_p)
+            K.permute4(w, wp, (R, in_p, 1, 1), (in_dim, 1, 0, 0))
+            self._packed[f"{m}.embed_pad"] = wp
+            for name, shape in [("embed.weight", (R, in_dim))] + [(f"lstm.{l}.weight_{k}", (4 * R, R)) for l in range(self.lstm_layers(m)) for k in ("ih", "hh")] + \
+                    ([("output.0.weight", (self.g, R))] if m == "frame_predictor" else []):
+                o, i = shape
+                wt = self.fbuf(f"{m}_{name}_T", o * i)
+                K.permute4(P[name], wt, (i, o, 1, 1), (1, i, 0, 0))
+                self._packed[f"{m}.{name}.T"] = wt
+
+    def lin_dinput(self, m, name, dY, out, rows, out_dim, in_dim, **kw):
+        """out[rows,in_dim] (+)= dY[rows,out_dim] . W[out_dim,in_dim]"""
+        if self.tc_lstm:
+            self.K.gemm(dY, self._packed[f"{m}.{name}.T"], out, rows, in_dim, out_dim, **kw)
+        else:
+            self.K.gemm(dY, self.arena[m].p[name], out, rows, in_dim, out_dim, b_mn=True, **kw)
+
+    def lin_wgrad(self, dY, X, gW, rows, out_dim, in_dim, ldx=None):
+        """gW[out_dim,in_dim] = dY[rows,out_dim]^T . X[rows,in_dim(+pad)]  (reduction over rows)"""
+        K = self.K
+        ldx = ldx or in_dim
+        if self.tc_lstm and out_dim % 8 == 0 and ldx % 8 == 0:
+            a = self.buf("wg_castA", rows * out_dim, torch.bfloat16)
+            b = self.buf("wg_castB", rows * ldx, torch.bfloat16)
+            K.permute4(dY, a, (rows * out_dim, 1, 1, 1), (1, 0, 0, 0))
+            K.permute4(X, b, (rows * ldx, 1, 1, 1), (1, 0, 0, 0))
+            K.gemm(a, b, gW, out_dim, in_dim, rows, a_mn=True, b_mn=True, lda=out_dim, ldb=ldx)
+        else:
+            K.gemm(dY, X, gW, out_dim, in_dim, rows, a_mn=True, b_mn=True, lda=out_dim, ldb=ldx)
 
     # ------------------------------------------------------------------ plan upload
     def upload_plan(self, plan):
@@ -259,7 +306,10 @@ class TrainEngine:
         return self._bufs["loss_out"][:4]
 
     def _run(self, x, plan):
+        if hasattr(self.K, "set_fp32_gemm_mode"):
+            self.K.set_fp32_gemm_mode(1 if self.tc_lstm else 0)
         self.pack_weights()
+        self.pack_lstm_weights()
         self.encode(x, plan)
         self.recurrent_fwd(plan)
         self.decode(plan)
@@ -268,6 +318,7 @@ class TrainEngine:
         if self.mode == "A":
             self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
             self.pack_weights(("decoder",))
+            self.pack_lstm_weights()
             self.backward_prior(plan)
         else:
             self.backward_prior(plan)
@@ -340,6 +391,10 @@ class TrainEngine:
         return st
 
     # -- Phase R ----------------------------------------------------------------------------
+    def in_pitch(self, in_dim):
+        """Row pitch of the LSTM input matrices: padded to a multiple of 8 floats in tensor-core mode."""
+        return (in_dim + 7) // 8 * 8 if self.tc_lstm else in_dim
+
     def lstm_layers(self, m):
         return len({k.split(".")[1] for k in self.arena[m].p if k.startswith("lstm.")})
 
@@ -351,8 +406,12 @@ class TrainEngine:
         L = self.lstm_layers(m)
         rows = steps * B
         E = self.fbuf(f"{m}_E", rows * R)
-        K.gemm(X, P["embed.weight"], E, rows, R, in_dim, bias=P["embed.bias"])
-        sv = dict(X=X, E=E, steps=steps, in_dim=in_dim, layers=[])
+        ldx = self.in_pitch(in_dim)
+        if self.tc_lstm:
+            K.gemm(X, self._packed[f"{m}.embed_pad"], E, rows, R, ldx, bias=P["embed.bias"])
+        else:
+            K.gemm(X, P["embed.weight"], E, rows, R, in_dim, bias=P["embed.bias"])
+        sv = dict(X=X, E=E, steps=steps, in_dim=in_dim, ldx=ldx, layers=[])
         inp = E
         for l in range(L):
             Pre = self.fbuf(f"{m}_pre{l}", rows * 4 * R)
@@ -378,10 +437,11 @@ class TrainEngine:
         H = self.Hlat
         ix = self.ix
         win = 2 * g + 2
-        Xpost = self.fbuf("Xpost", S * B * win)
-        Xprior = self.fbuf("Xprior", S * B * win)
-        K.build_concat(Xpost, H, ix["tgt_idx"], g, H, ix["glob_idx"], g, self.tuc, self.dt, S, B)
-        K.build_concat(Xprior, H, ix["in_idx"], g, H, ix["glob_idx"], g, self.tuc, self.dt, S, B)
+        lw = self.in_pitch(win)
+        Xpost = self.fbuf("Xpost", S * B * lw)
+        Xprior = self.fbuf("Xprior", S * B * lw)
+        K.build_concat(Xpost, H, ix["tgt_idx"], g, H, ix["glob_idx"], g, self.tuc, self.dt, S, B, ld=lw)
+        K.build_concat(Xprior, H, ix["in_idx"], g, H, ix["glob_idx"], g, self.tuc, self.dt, S, B, ld=lw)
         self.sv = {}
         heads = {}
         for m, X in (("posterior", Xpost), ("prior", Xprior)):
@@ -407,8 +467,8 @@ class TrainEngine:
         K.permute4(self.Zp[(S - 1) * B * z:], self.Zall[S * B * z:], (B * z, 1, 1, 1), (1, 0, 0, 0))
         # frame predictor over S recon steps + the CPC step (models/p2p_model.py:247,252)
         wp = g + z + 2
-        Xpred = self.fbuf("Xpred", (S + 1) * B * wp)
-        K.build_concat(Xpred, H, ix["in_idx"], g, self.Zall, ix["z_idx"], z, self.tuc, self.dt, S + 1, B)
+        Xpred = self.fbuf("Xpred", (S + 1) * B * self.in_pitch(wp))
+        K.build_concat(Xpred, H, ix["in_idx"], g, self.Zall, ix["z_idx"], z, self.tuc, self.dt, S + 1, B, ld=self.in_pitch(wp))
         sv = self.lstm_forward("frame_predictor", Xpred, S + 1, wp)
         self.sv["frame_predictor"] = sv
         P = self.arena["frame_predictor"].p
@@ -573,7 +633,7 @@ class TrainEngine:
                 dh_s = dH[s * B * R:(s + 1) * B * R]
                 if s < steps - 1:
                     # dh_total = dH[s] + dG[s+1] . W_hh
-                    K.gemm(dG[(s + 1) * B * 4 * R:(s + 2) * B * 4 * R], whh, dht, B, R, 4 * R, b_mn=True, addend=dh_s)
+                    self.lin_dinput(m, f"lstm.{l}.weight_hh", dG[(s + 1) * B * 4 * R:(s + 2) * B * 4 * R], dht, B, 4 * R, R, addend=dh_s)
                     dh_s = dht
                 dc_prev = dcA if (s % 2 == 0) else dcB
                 K.lstm_pointwise_bwd(dh_s, dc_next, lay["gates"][s * B * 4 * R:(s + 1) * B * 4 * R],
@@ -581,21 +641,21 @@ class TrainEngine:
                                      dG[s * B * 4 * R:(s + 1) * B * 4 * R], dc_prev, B, R)
                 dc_next = dc_prev
             if want_wgrad:
-                K.gemm(dG, lay["hs"], A.g[f"lstm.{l}.weight_hh"], 4 * R, R, rows, a_mn=True, b_mn=True, lda=4 * R, ldb=R)
-                K.gemm(dG, lay["inp"], A.g[f"lstm.{l}.weight_ih"], 4 * R, R, rows, a_mn=True, b_mn=True, lda=4 * R, ldb=R)
+                self.lin_wgrad(dG, lay["hs"], A.g[f"lstm.{l}.weight_hh"], rows, 4 * R, R)
+                self.lin_wgrad(dG, lay["inp"], A.g[f"lstm.{l}.weight_ih"], rows, 4 * R, R)
                 K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_ih"])
                 K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_hh"])
             dIn = self.fbuf(f"{m}_dIn{l}", rows * R)
-            K.gemm(dG, P[f"lstm.{l}.weight_ih"], dIn, rows, R, 4 * R, b_mn=True)
+            self.lin_dinput(m, f"lstm.{l}.weight_ih", dG, dIn, rows, 4 * R, R)
             dH = dIn
         dE = dH
         in_dim = sv["in_dim"]
         if want_wgrad:
-            K.gemm(dE, sv["X"], A.g["embed.weight"], R, in_dim, rows, a_mn=True, b_mn=True, lda=R, ldb=in_dim)
+            self.lin_wgrad(dE, sv["X"], A.g["embed.weight"], rows, R, in_dim, ldx=sv["ldx"])
             K.colsum(dE, rows, R, R, A.g["embed.bias"])
         if want_dx:
             dX = dx_out if dx_out is not None else self.fbuf(f"{m}_dX", rows * in_dim)
-            K.gemm(dE, P["embed.weight"], dX, rows, in_dim, R, b_mn=True)
+            self.lin_dinput(m, "embed.weight", dE, dX, rows, R, in_dim)
             return dX
         return None
 
@@ -635,10 +695,10 @@ class TrainEngine:
         dpre = self.fbuf("pred_dpre", (S + 1) * B * g)
         K.act_bwd(self.d_hpred, self.h_pred, dpre, rows * g, ACT_TANH)
         top = self.sv["frame_predictor"]["top"]
-        K.gemm(dpre, top, A.g["output.0.weight"], g, R, rows, a_mn=True, b_mn=True, lda=g, ldb=R)
+        self.lin_wgrad(dpre, top, A.g["output.0.weight"], rows, g, R)
         K.colsum(dpre, rows, g, g, A.g["output.0.bias"])
         dtop = self.fbuf("pred_dtop", (S + 1) * B * R)
-        K.gemm(dpre, A.p["output.0.weight"], dtop, rows, R, g, b_mn=True)
+        self.lin_dinput("frame_predictor", "output.0.weight", dpre, dtop, rows, g, R)
         wp = g + z + 2
         dXpred = self.lstm_backward("frame_predictor", dtop, S, want_wgrad=True, want_dx=True)
         # posterior / prior seeds: d z_post from the predictor input, beta * dKL
@@ -723,7 +783,7 @@ class TrainEngine:
             dpre = self.fbuf("cpc_dpre", B * g)
             K.act_bwd(self.d_hpred[S * B * g:], self.h_pred[S * B * g:], dpre, B * g, ACT_TANH)
             dh = self.fbuf("cpc_dh", B * R)
-            K.gemm(dpre, A.p["output.0.weight"], dh, B, R, g, b_mn=True)
+            self.lin_dinput("frame_predictor", "output.0.weight", dpre, dh, B, g, R)
             L = len(sv["layers"])
             dG = self.fbuf("cpc_dG", B * 4 * R)
             dcp = self.fbuf("cpc_dc", B * R)
@@ -732,11 +792,11 @@ class TrainEngine:
                 K.lstm_pointwise_bwd(dh, None, lay["gates"][S * B * 4 * R:(S + 1) * B * 4 * R], lay["cs"][S * B * R:(S + 1) * B * R],
                                      lay["cs"][(S + 1) * B * R:(S + 2) * B * R], dG, dcp, B, R)
                 dh2 = self.fbuf(f"cpc_dh{l}", B * R)
-                K.gemm(dG, A.p[f"lstm.{l}.weight_ih"], dh2, B, R, 4 * R, b_mn=True)
+                self.lin_dinput("frame_predictor", f"lstm.{l}.weight_ih", dG, dh2, B, 4 * R, R)
                 dh = dh2
             wp = g + z + 2
             dX = self.fbuf("cpc_dX", B * wp)
-            K.gemm(dh, A.p["embed.weight"], dX, B, wp, R, b_mn=True)
+            self.lin_dinput("frame_predictor", "embed.weight", dh, dX, B, R, wp)
             K.permute4(dX[g:], dzp[(S - 1) * B * z:], (B, z, 1, 1), (wp, 1, 0, 0))
         dmu, dlv, dmu_p, dlv_p = (self.fbuf(nm, n) for nm in ("dmu", "dlv", "dmu_p", "dlv_p"))
         K.reparam_kl_bwd(self.mu, self.lv, self.mu_p, self.lv_p, self.eps_post, self.eps_prior, None, dzp,

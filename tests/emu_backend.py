@@ -213,14 +213,18 @@ class EmuKernels:
         for t, s in ((dmu, gm1), (dlv, gl1), (dmu_p, gm2), (dlv_p, gl2)):
             _flat(t, n).copy_(s)
 
-    def build_concat(self, dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B):
+    def build_concat(self, dst, A, ia, ga, Bm, ib, gb, tuc, dt, S, B, ld=None):
         Av = _flat(A, A.numel()).reshape(-1, B, ga)
         Bv = _flat(Bm, Bm.numel()).reshape(-1, B, gb)
         a = Av[ia[:S].long()]
         b = Bv[ib[:S].long()]
         t1 = tuc[:S].reshape(S, 1, 1).expand(S, B, 1)
         t2 = dt[:S].reshape(S, 1, 1).expand(S, B, 1)
-        _flat(dst, S * B * (ga + gb + 2)).copy_(torch.cat([a, b, t1, t2], 2).reshape(-1))
+        W = ga + gb + 2
+        ld = ld if ld is not None else W
+        d = _flat(dst, S * B * ld).reshape(S * B, ld)
+        d.zero_()
+        d[:, :W] = torch.cat([a, b, t1, t2], 2).reshape(S * B, W)
 
     def gather_add_cols(self, dst, src, idx, S, T, B, g, W, col0, init=False):
         d = _flat(dst, T * B * g).reshape(T, B, g)
