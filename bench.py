@@ -243,7 +243,7 @@ def main():
                 a.record()
                 orig(A, Bm, C, M, N, Kd, **kw)
                 b.record()
-                rec.append((a, b, 2.0 * M * N * Kd))
+                rec.append((a, b, 2.0 * M * N * Kd, (M, N, Kd, bool(kw.get("a_mn")), bool(kw.get("b_mn")), str(C.dtype))))
             else:
                 orig(A, Bm, C, M, N, Kd, **kw)
 
@@ -251,8 +251,11 @@ def main():
         eng.step(x_dev, use_graph=False, return_device=True)
         torch.cuda.synchronize()
         K.gemm = orig
-        tms = sum(a.elapsed_time(b) for a, b, _ in rec)
-        fl = sum(f for _, _, f in rec)
+        tms = sum(r[0].elapsed_time(r[1]) for r in rec)
+        fl = sum(r[2] for r in rec)
+        if os.environ.get("P2PVG_DUMP_GEMMS"):
+            rows = [dict(shape=r[3], ms=r[0].elapsed_time(r[1]), tflops=r[2] / (r[0].elapsed_time(r[1]) * 1e-3) / 1e12) for r in rec]
+            json.dump(rows, open(os.environ["P2PVG_DUMP_GEMMS"], "w"))
         pk = peaks()
         ach = fl / (tms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05.mma kind::f16, TMA-staged, TMEM accumulators)",

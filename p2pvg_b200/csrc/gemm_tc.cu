@@ -28,7 +28,7 @@ template <int BN> struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 128) ? 6 : 8;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -111,41 +111,52 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 // ------------------------------------------------------------------ the kernel
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...  A tile is
+// (split z, m-tile, n-tile) with the n-tile fastest, so CTAs running at the same time share the A rows in L2.
+// The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of tile i+1.
 template <typename TIn, int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv,
                int c_bf16, long long ldc, int M, int N, int K, int accumulate, const float* __restrict__ bias,
-               const void* __restrict__ addend, long long ldd, float* __restrict__ partial, int kb_per_split) {
+               const void* __restrict__ addend, long long ldd, float* __restrict__ partial, int kb_per_split, int splits) {
   using C_ = Cfg<BN>;
   constexpr int ELEM = sizeof(TIn);
   constexpr int BLOCK_K = ROW_BYTES / ELEM;  // elements of K per pipeline stage (K-major) / rows per stage (MN-major)
   constexpr int UMMA_K = 32 / ELEM;          // K per tcgen05.mma: 16 for bf16, 8 for tf32
   constexpr bool TF32 = (ELEM == 4);
+  constexpr uint32_t TMEM_COLS = 2 * BN;
   static_assert(!(TF32 && (A_MN || B_MN)), "tf32 path supports K-major operands only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C_::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C_::STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + C_::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BN;
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M, tiles_n = (N + BN - 1) / BN;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int num_tiles = tiles_mn * splits;
   const int nkb_total = (K + BLOCK_K - 1) / BLOCK_K;
-  const int kb0 = blockIdx.z * kb_per_split;
-  const int kb1 = min(kb0 + kb_per_split, nkb_total);
-  const int nkb = kb1 - kb0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C_::STAGES; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -157,147 +168,175 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int i = 0; i < nkb; i++) {
-        const int s = i % C_::STAGES;
-        const uint32_t ph = (i / C_::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * C_::STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
-        const int k0 = (kb0 + i) * BLOCK_K;
-        if (A_MN) {
-          tma_load_2d(&tmA, &full_bar[s], sa, m0, k0);
-          tma_load_2d(&tmA, &full_bar[s], sa + BLOCK_K * 128, m0 + 64, k0);
-        } else {
-          tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);
-        }
-        if (B_MN) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int z = t / tiles_mn, r = t - z * tiles_mn;
+        const int m0 = (r / tiles_n) * BLOCK_M, n0 = (r % tiles_n) * BN;
+        const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          const int s = it % C_::STAGES;
+          const uint32_t ph = (it / C_::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * C_::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (A_MN) {
+            tma_load_2d(&tmA, &full_bar[s], sa, m0, k0);
+            tma_load_2d(&tmA, &full_bar[s], sa + BLOCK_K * 128, m0 + 64, k0);
+          } else {
+            tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; j++) tma_load_2d(&tmB, &full_bar[s], sb + j * BLOCK_K * 128, n0 + 64 * j, k0);
-        } else {
-          tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);
+            for (int j = 0; j < BN / 64; j++) tma_load_2d(&tmB, &full_bar[s], sb + j * BLOCK_K * 128, n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
-      const uint32_t fmt = TF32 ? 2u : 1u;  // operand format: 1 = bf16, 2 = tf32
+      // instruction descriptor: D=f32, operand format, majors, N>>3, M>>4
+      const uint32_t fmt = TF32 ? 2u : 1u;  // 1 = bf16, 2 = tf32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-      for (int i = 0; i < nkb; i++) {
-        const int s = i % C_::STAGES;
-        const uint32_t ph = (i / C_::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
+        const int z = t / tiles_mn;
+        const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
+        const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t tmem_c = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          const int s = it % C_::STAGES;
+          const uint32_t ph = (it / C_::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-          // K-major: 16 bf16 = 32 B further inside the 128 B swizzle row; MN-major: 16 rows of 128 B further
-          const uint64_t da = A_MN ? make_desc(sa + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sa + k * 32, 0, 1024);
-          const uint64_t db = B_MN ? make_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sb + k * 32, 0, 1024);
-          if (TF32) umma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          else umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+            // K-major: 32 B further inside the 128 B swizzle row; MN-major: UMMA_K rows of 128 B further
+            const uint64_t da = A_MN ? make_desc(sa + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sa + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024) : make_desc(sb + k * 32, 0, 1024);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (TF32) umma_tf32(tmem_c, da, db, idesc, accum);
+            else umma_bf16(tmem_c, da, db, idesc, accum);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&tmem_full_bar[acc]);  // accumulator of this tile complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const long long m = (long long)m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const bool row_ok = m < M;
     const bool split = (partial != nullptr);
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
+      const int z = t / tiles_mn, r = t - z * tiles_mn;
+      const int m0 = (r / tiles_n) * BLOCK_M, n0 = (r % tiles_n) * BN;
+      const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
+      const long long m = (long long)m0 + q * 32 + lane;
+      const bool row_ok = m < M;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int nbase = n0 + c * 32;
-      if (!row_ok || nbase >= N) continue;
-      if (nkb <= 0) {
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        const int nbase = n0 + c * 32;
+        if (!row_ok || nbase >= N) continue;
+        if (split) {
+          float* dst = partial + ((long long)z * M + m) * N + nbase;
+          if (nbase + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = 0u;
-      }
-      if (split) {
-        float* dst = partial + ((long long)blockIdx.z * M + m) * N + nbase;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
 #pragma unroll
-        for (int j = 0; j < 32; j++)
-          if (nbase + j < N) dst[j] = __uint_as_float(v[j]);
-        continue;
-      }
-      float f[32];
+            for (int j = 0; j < 32; j++)
+              if (nbase + j < N) dst[j] = __uint_as_float(v[j]);
+          }
+          continue;
+        }
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-      if (bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j++)
-          if (nbase + j < N) f[j] += bias[nbase + j];
-      }
-      if (c_bf16) {
-        bf16* crow = reinterpret_cast<bf16*>(Cv) + m * ldc + nbase;
-        if (addend) {
-          const bf16* arow = reinterpret_cast<const bf16*>(addend) + m * ldd + nbase;
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        if (bias) {
 #pragma unroll
           for (int j = 0; j < 32; j++)
-            if (nbase + j < N) f[j] += __bfloat162float(arow[j]);
+            if (nbase + j < N) f[j] += bias[nbase + j];
         }
-        if (accumulate) {
+        if (c_bf16) {
+          bf16* crow = reinterpret_cast<bf16*>(Cv) + m * ldc + nbase;
+          if (addend) {
+            const bf16* arow = reinterpret_cast<const bf16*>(addend) + m * ldd + nbase;
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (nbase + j < N) f[j] += __bfloat162float(crow[j]);
-        }
-        const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-        if (vec) {
+            for (int j = 0; j < 32; j++)
+              if (nbase + j < N) f[j] += __bfloat162float(arow[j]);
+          }
+          if (accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&p0);
-            pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2);
-            pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(crow + j) = pk;
+            for (int j = 0; j < 32; j++)
+              if (nbase + j < N) f[j] += __bfloat162float(crow[j]);
+          }
+          const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&p0);
+              pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2);
+              pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(crow + j) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (nbase + j < N) crow[j] = __float2bfloat16_rn(f[j]);
           }
         } else {
+          float* crow = reinterpret_cast<float*>(Cv) + m * ldc + nbase;
+          if (addend) {
+            const float* arow = reinterpret_cast<const float*>(addend) + m * ldd + nbase;
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (nbase + j < N) crow[j] = __float2bfloat16_rn(f[j]);
-        }
-      } else {
-        float* crow = reinterpret_cast<float*>(Cv) + m * ldc + nbase;
-        if (addend) {
-          const float* arow = reinterpret_cast<const float*>(addend) + m * ldd + nbase;
+            for (int j = 0; j < 32; j++)
+              if (nbase + j < N) f[j] += arow[j];
+          }
+          if (accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (nbase + j < N) f[j] += arow[j];
-        }
-        if (accumulate) {
+            for (int j = 0; j < 32; j++)
+              if (nbase + j < N) f[j] += crow[j];
+          }
+          const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+          if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (nbase + j < N) f[j] += crow[j];
-        }
-        const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-        if (vec) {
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (nbase + j < N) crow[j] = f[j];
+            for (int j = 0; j < 32; j++)
+              if (nbase + j < N) crow[j] = f[j];
+          }
         }
       }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): hand the accumulator back
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -326,7 +365,12 @@ EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 int g_attr_done[2][2][2][2] = {};
 
+int g_num_sms = 148;
+
 void resolve_driver() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    g_num_sms = sms;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
@@ -363,9 +407,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, l
     }
     done = 1;
   }
-  dim3 grid(cdiv(M, BLOCK_M), cdiv(N, BN), splits);
+  long long num_tiles = (long long)cdiv(M, BLOCK_M) * cdiv(N, BN) * splits;
+  int grid = (int)(num_tiles < g_num_sms ? num_tiles : g_num_sms);
   kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, C, c_dtype == P2PVG_BF16, ldc, M, N, K, accumulate, bias, addend, ldd,
-                                                      partial, kb_per_split);
+                                                      partial, kb_per_split, splits);
   return p2pvg_check_launch("gemm_tc");
 }
 

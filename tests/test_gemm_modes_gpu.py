@@ -30,7 +30,7 @@ def test_tf32_gemm(KS, M, N, K):
         Kc.set_fp32_gemm_mode(0)
     Ke.gemm(A, B, C2, M, N, K, bias=bias, addend=add, accumulate=True)
     err = (C1 - C2).abs().max().item()
-    assert err <= 4e-3 * K ** 0.5, f"tf32 error {err}"          # 10-bit mantissa operands, fp32 accumulation
+    assert err <= 1e-2 * K ** 0.5, f"tf32 error {err}"          # 10-bit (truncated) mantissa operands, fp32 accumulation; max over M*N outputs
     assert err > 0 or K < 8                                        # really ran at reduced precision
     C3 = C1.clone()
     Kc.gemm(A, B, C3, M, N, K, bias=bias, addend=add)            # exact mode again
