@@ -15,73 +15,77 @@ __device__ __forceinline__ float act_grad(float y, int act) {
 }
 
 // MODE 0: (sum x, sum x^2).  MODE 1: (sum dz, sum dz*xhat), dz = dy*act'(y), xhat=(x-mean)*invstd
+// 16-byte vectors along the channel axis (V = 8 bf16 / 4 fp32 channels per thread), 256/CV row lanes per block.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                                                         long long R, int C, int rows_per_chunk, double2* __restrict__ partial) {
-  const int CV = C >> 2;
+  constexpr int V = VecN<T>::N;
+  const int CV = C / V;
   const int lanes = 256 / CV;
   const int cv = threadIdx.x % CV, lane = threadIdx.x / CV;
   const int g = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const long long r0 = (long long)chunk * rows_per_chunk;
   long long r1 = r0 + rows_per_chunk;
   if (r1 > R) r1 = R;
-  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-  float mu[4] = {0, 0, 0, 0}, is[4] = {0, 0, 0, 0};
-  if (MODE == 1) {
+  float s0[V], s1[V], mu[V], is[V];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      mu[j] = mean[(long long)g * C + cv * 4 + j];
-      is[j] = invstd[(long long)g * C + cv * 4 + j];
+  for (int j = 0; j < V; j++) {
+    s0[j] = 0.f; s1[j] = 0.f; mu[j] = 0.f; is[j] = 0.f;
+    if (MODE == 1) {
+      mu[j] = mean[(long long)g * C + cv * V + j];
+      is[j] = invstd[(long long)g * C + cv * V + j];
     }
   }
-  if (lane < lanes) {
-    for (long long r = r0 + lane; r < r1; r += lanes) {
-      const long long off = ((long long)g * R + r) * C + cv * 4;
-      f4 xv = ld_f4<T>(x + off);
-      if (MODE == 0) {
+  for (long long r = r0 + lane; r < r1; r += 2 * lanes) {
+    // two rows per iteration: all loads issued before use
+    const long long off0 = ((long long)g * R + r) * C + cv * V;
+    const bool two = (r + lanes) < r1;
+    const long long off1 = off0 + (long long)lanes * C;
+    uint4 xa = ld_raw16(x + off0), xb = two ? ld_raw16(x + off1) : make_uint4(0u, 0u, 0u, 0u);
+    uint4 da, db, ya, yb;
+    if (MODE == 1) {
+      da = ld_raw16(dy + off0);
+      ya = ld_raw16(y + off0);
+      db = two ? ld_raw16(dy + off1) : make_uint4(0u, 0u, 0u, 0u);
+      yb = two ? ld_raw16(y + off1) : make_uint4(0u, 0u, 0u, 0u);
+    }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          s0[j] += xv.v[j];
-          s1[j] = fmaf(xv.v[j], xv.v[j], s1[j]);
-        }
-      } else {
-        f4 dv = ld_f4<T>(dy + off);
-        f4 yv = ld_f4<T>(y + off);
+    for (int h = 0; h < 2; h++) {
+      if (h == 1 && !two) break;
+      float xv[V], dv[V], yv[V];
+      unpack16<T>(h ? xb : xa, xv);
+      if (MODE == 1) {
+        unpack16<T>(h ? db : da, dv);
+        unpack16<T>(h ? yb : ya, yv);
+      }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          float dz = dv.v[j] * act_grad(yv.v[j], act);
+      for (int j = 0; j < V; j++) {
+        if (MODE == 0) {
+          s0[j] += xv[j];
+          s1[j] = fmaf(xv[j], xv[j], s1[j]);
+        } else {
+          float dz = dv[j] * act_grad(yv[j], act);
           s0[j] += dz;
-          s1[j] = fmaf(dz, (xv.v[j] - mu[j]) * is[j], s1[j]);
+          s1[j] = fmaf(dz, (xv[j] - mu[j]) * is[j], s1[j]);
         }
       }
     }
   }
-  __shared__ double sh0[256 * 4];
-  __shared__ double sh1[256 * 4];
+  __shared__ float sh0[256 * V];
+  __shared__ float sh1[256 * V];
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    sh0[threadIdx.x * 4 + j] = (lane < lanes) ? (double)s0[j] : 0.0;
-    sh1[threadIdx.x * 4 + j] = (lane < lanes) ? (double)s1[j] : 0.0;
+  for (int j = 0; j < V; j++) {
+    sh0[threadIdx.x * V + j] = s0[j];
+    sh1[threadIdx.x * V + j] = s1[j];
   }
   __syncthreads();
-  if (threadIdx.x < C) {
-    // channel c = threadIdx.x: vector cvv = c/4, component j = c%4; sum over lanes
-    const int cvv = threadIdx.x >> 2, j = threadIdx.x & 3;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int cvv = c / V, j = c % V;
     double a = 0.0, b = 0.0;
     for (int l = 0; l < lanes; l++) {
-      a += sh0[(l * CV + cvv) * 4 + j];
-      b += sh1[(l * CV + cvv) * 4 + j];
-    }
-    partial[((long long)g * nchunk + chunk) * C + threadIdx.x] = make_double2(a, b);
-  }
-  // C can exceed 256 threads? No: C/4 <= 256 but C may be up to 1024 -> loop
-  for (int c = threadIdx.x + 256; c < C; c += 256) {
-    const int cvv = c >> 2, j = c & 3;
-    double a = 0.0, b = 0.0;
-    for (int l = 0; l < lanes; l++) {
-      a += sh0[(l * CV + cvv) * 4 + j];
-      b += sh1[(l * CV + cvv) * 4 + j];
+      a += (double)sh0[(l * CV + cvv) * V + j];
+      b += (double)sh1[(l * CV + cvv) * V + j];
     }
     partial[((long long)g * nchunk + chunk) * C + c] = make_double2(a, b);
   }
@@ -128,53 +132,66 @@ __global__ void bn_bwd_finalize_kernel(const double2* __restrict__ partial, int 
 }
 
 template <typename T>
-__global__ void bn_act_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
-                              const float* __restrict__ shift, long long R, int C, long long total4, int act) {
-  const int CV = C >> 2;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    long long row = idx / CV;
-    int g = (int)(row / R);
-    f4 v = ld_f4<T>(x + idx * 4);
-    const float4 sc = *reinterpret_cast<const float4*>(scale + (long long)g * C + cv * 4);
-    const float4 sh = *reinterpret_cast<const float4*>(shift + (long long)g * C + cv * 4);
-    float s[4] = {sc.x, sc.y, sc.z, sc.w}, h[4] = {sh.x, sh.y, sh.z, sh.w};
+__global__ void __launch_bounds__(256) bn_act_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, long long R, int C, long long totalv, int act) {
+  constexpr int V = VecN<T>::N;
+  const int CV = C / V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < totalv; base += 2 * stride) {
+    uint4 raw[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      float z = fmaf(v.v[j], s[j], h[j]);
-      if (act == P2PVG_ACT_LRELU) z = z > 0.f ? z : 0.2f * z;
-      else if (act == P2PVG_ACT_TANH) z = tanhf(z);
-      v.v[j] = z;
+    for (int u = 0; u < 2; u++) {
+      const long long idx = base + u * stride;
+      if (idx < totalv) raw[u] = ld_raw16(x + idx * V);
     }
-    st_f4<T>(y + idx * 4, v);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long idx = base + u * stride;
+      if (idx >= totalv) continue;
+      const int cv = (int)(idx % CV);
+      const int g = (int)((idx / CV) / R);
+      float v[V];
+      unpack16<T>(raw[u], v);
+      const float* sc = scale + (long long)g * C + cv * V;
+      const float* sh = shift + (long long)g * C + cv * V;
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        float z = fmaf(v[j], sc[j], sh[j]);
+        if (act == P2PVG_ACT_LRELU) z = z > 0.f ? z : 0.2f * z;
+        else if (act == P2PVG_ACT_TANH) z = tanhf(z);
+        v[j] = z;
+      }
+      st_raw16(y + idx * V, pack16<T>(v));
+    }
   }
 }
 
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ sum_dz,
-                                    const float* __restrict__ sum_dzx, long long R, int C, long long total4, int act,
-                                    T* __restrict__ dx) {
-  const int CV = C >> 2;
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ sum_dz,
+                                                           const float* __restrict__ sum_dzx, long long R, int C, long long totalv,
+                                                           int act, T* __restrict__ dx) {
+  constexpr int V = VecN<T>::N;
+  const int CV = C / V;
   const float invR = 1.f / (float)R;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    long long row = idx / CV;
-    int g = (int)(row / R);
-    f4 dv = ld_f4<T>(dy + idx * 4);
-    f4 xv = ld_f4<T>(x + idx * 4);
-    f4 yv = ld_f4<T>(y + idx * 4);
-    f4 o;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < totalv; idx += (long long)gridDim.x * blockDim.x) {
+    const uint4 rd = ld_raw16(dy + idx * V), rx = ld_raw16(x + idx * V), ry = ld_raw16(y + idx * V);
+    const int cv = (int)(idx % CV);
+    const int g = (int)((idx / CV) / R);
+    float dv[V], xv[V], yv[V], o[V];
+    unpack16<T>(rd, dv);
+    unpack16<T>(rx, xv);
+    unpack16<T>(ry, yv);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const long long gc = (long long)g * C + cv * 4 + j;
-      float is = invstd[gc];
-      float xhat = (xv.v[j] - mean[gc]) * is;
-      float dz = dv.v[j] * act_grad(yv.v[j], act);
-      o.v[j] = gamma[cv * 4 + j] * is * (dz - sum_dz[gc] * invR - xhat * sum_dzx[gc] * invR);
+    for (int j = 0; j < V; j++) {
+      const long long gc = (long long)g * C + cv * V + j;
+      const float is = invstd[gc];
+      const float xhat = (xv[j] - mean[gc]) * is;
+      const float dz = dv[j] * act_grad(yv[j], act);
+      o[j] = gamma[cv * V + j] * is * (dz - sum_dz[gc] * invR - xhat * sum_dzx[gc] * invR);
     }
-    st_f4<T>(dx + idx * 4, o);
+    st_raw16(dx + idx * V, pack16<T>(o));
   }
 }
 
@@ -208,15 +225,15 @@ __global__ void bn_ema_kernel(float* __restrict__ rmean, float* __restrict__ rva
 
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
-  const long long cap = 148LL * 32;
+  const long long cap = 148LL * 64;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
 struct Chunking {
   int nchunk, rows_per_chunk;
 };
-inline Chunking choose_chunks(long long R, int C) {
-  int lanes = 256 / (C / 4);
+inline Chunking choose_chunks(long long R, int C, int vec) {
+  int lanes = 256 / (C / vec);
   if (lanes < 1) lanes = 1;
   long long want = (R + (long long)lanes * 16 - 1) / ((long long)lanes * 16);  // >=16 rows per thread
   int nchunk = (int)(want < 1 ? 1 : (want > BN_MAXCHUNK ? BN_MAXCHUNK : want));
@@ -225,10 +242,10 @@ inline Chunking choose_chunks(long long R, int C) {
   return Chunking{nchunk, rpc};
 }
 
-inline int check_bn_shape(int C, const char* what) {
-  int CV = C / 4;
-  if (C % 4 != 0 || CV > 256 || (256 % CV) != 0) {
-    p2pvg_set_error("%s: unsupported channel count %d (need C%%4==0, C/4 a divisor of 256)", what, C);
+inline int check_bn_shape(int C, int vec, const char* what) {
+  int CV = C / vec;
+  if (C % vec != 0 || CV < 1 || CV > 256 || (256 % CV) != 0) {
+    p2pvg_set_error("%s: unsupported channel count %d (need C a multiple of the 16-byte vector, C/vec a divisor of 256)", what, C);
     return P2PVG_ERR_UNSUPPORTED;
   }
   return P2PVG_OK;
@@ -241,10 +258,11 @@ size_t p2pvg_bn_workspace_bytes_impl(int G, int C) { return (size_t)G * BN_MAXCH
 int p2pvg_bn_fwd_stats_impl(const void* x, int dtype, int G, long long R, int C, const float* gamma, const float* beta, float eps,
                             void* ws, size_t ws_bytes, float* mean, float* invstd, float* var_unbiased, float* scale,
                             float* shift, cudaStream_t st) {
-  if (int e = check_bn_shape(C, "bn_fwd_stats")) return e;
+  const int vec = dtype == P2PVG_BF16 ? 8 : 4;
+  if (int e = check_bn_shape(C, vec, "bn_fwd_stats")) return e;
   P2PVG_REQUIRE(ws_bytes >= p2pvg_bn_workspace_bytes_impl(G, C), P2PVG_ERR_WORKSPACE, "bn_fwd_stats: workspace too small");
   if (G == 0) return P2PVG_OK;
-  Chunking ch = choose_chunks(R, C);
+  Chunking ch = choose_chunks(R, C, vec);
   dim3 grid(ch.nchunk, G);
   DISPATCH_DTYPE(dtype, T, (bn_reduce_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, 0, R, C,
                                                                          ch.rows_per_chunk, (double2*)ws)));
@@ -255,27 +273,29 @@ int p2pvg_bn_fwd_stats_impl(const void* x, int dtype, int G, long long R, int C,
 
 int p2pvg_bn_act_impl(const void* x, void* y, int dtype, const float* scale, const float* shift, int G, long long R, int C, int act,
                       cudaStream_t st) {
-  P2PVG_REQUIRE(C % 4 == 0, P2PVG_ERR_UNSUPPORTED, "bn_act: C %% 4 != 0");
-  long long total4 = (long long)G * R * (C / 4);
-  if (total4 == 0) return P2PVG_OK;
-  DISPATCH_DTYPE(dtype, T, (bn_act_kernel<T><<<grid_for(total4, 256), 256, 0, st>>>((const T*)x, (T*)y, scale, shift, R, C, total4, act)));
+  const int vec = dtype == P2PVG_BF16 ? 8 : 4;
+  P2PVG_REQUIRE(C % vec == 0, P2PVG_ERR_UNSUPPORTED, "bn_act: C not a multiple of the 16-byte vector");
+  long long totalv = (long long)G * R * (C / vec);
+  if (totalv == 0) return P2PVG_OK;
+  DISPATCH_DTYPE(dtype, T, (bn_act_kernel<T><<<grid_for((totalv + 1) / 2, 256), 256, 0, st>>>((const T*)x, (T*)y, scale, shift, R, C, totalv, act)));
   return p2pvg_check_launch("bn_act");
 }
 
 int p2pvg_bn_bwd_impl(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
                       const float* gamma, int G, long long R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
                       float* sum_dzx, cudaStream_t st) {
-  if (int e = check_bn_shape(C, "bn_bwd")) return e;
+  const int vec = dtype == P2PVG_BF16 ? 8 : 4;
+  if (int e = check_bn_shape(C, vec, "bn_bwd")) return e;
   P2PVG_REQUIRE(ws_bytes >= p2pvg_bn_workspace_bytes_impl(G, C), P2PVG_ERR_WORKSPACE, "bn_bwd: workspace too small");
   if (G == 0) return P2PVG_OK;
-  Chunking ch = choose_chunks(R, C);
+  Chunking ch = choose_chunks(R, C, vec);
   dim3 grid(ch.nchunk, G);
   DISPATCH_DTYPE(dtype, T, (bn_reduce_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, act, R, C,
                                                                          ch.rows_per_chunk, (double2*)ws)));
   bn_bwd_finalize_kernel<<<cdiv((long long)G * C, 256), 256, 0, st>>>((const double2*)ws, ch.nchunk, G, C, sum_dz, sum_dzx);
-  long long total4 = (long long)G * R * (C / 4);
-  DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<grid_for(total4, 256), 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, mean, invstd,
-                                                                                          gamma, sum_dz, sum_dzx, R, C, total4, act, (T*)dx)));
+  long long totalv = (long long)G * R * (C / vec);
+  DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<grid_for(totalv, 256), 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, mean, invstd,
+                                                                                          gamma, sum_dz, sum_dzx, R, C, totalv, act, (T*)dx)));
   return p2pvg_check_launch("bn_bwd");
 }
 

@@ -65,6 +65,40 @@ template <> __device__ __forceinline__ void st_f4<bf16>(bf16* p, const f4& x) {
   *reinterpret_cast<uint2*>(p) = t;
 }
 
+// 16-byte vectors: 4 floats or 8 bf16.  VecN<T>::N elements per vector.
+template <typename T> struct VecN;
+template <> struct VecN<float> { static constexpr int N = 4; };
+template <> struct VecN<bf16> { static constexpr int N = 8; };
+
+__device__ __forceinline__ uint4 ld_raw16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st_raw16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+template <typename T> __device__ __forceinline__ void unpack16(uint4 r, float* f);
+template <> __device__ __forceinline__ void unpack16<float>(uint4 r, float* f) {
+  f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+}
+template <> __device__ __forceinline__ void unpack16<bf16>(uint4 r, float* f) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {  // bf16 -> fp32 is a 16-bit shift
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <typename T> __device__ __forceinline__ uint4 pack16(const float* f);
+template <> __device__ __forceinline__ uint4 pack16<float>(const float* f) {
+  return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+template <> __device__ __forceinline__ uint4 pack16<bf16>(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&p);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

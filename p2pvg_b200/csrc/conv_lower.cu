@@ -7,13 +7,47 @@
 namespace {
 
 // ---- im2col: x [N,H,W,C] -> col [N*(H/2)*(W/2), 16*C], K order (kh, kw, c) ----------------------
-template <typename T, int V>
-__global__ void im2col_k4s2p1_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C) {
+// 16-byte vectors (8 bf16 / 4 fp32), four independent copies in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_vec_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C) {
+  constexpr int V = VecN<T>::N;
   const int Ho = H >> 1, Wo = W >> 1, CV = C / V;
   const long long total = (long long)N * Ho * Wo * 16 * CV;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long idx = base + u * stride;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < total) {
+        const int cv = (int)(idx % CV);
+        const long long r = idx / CV;
+        const int tap = (int)(r & 15);
+        const long long row = r >> 4;
+        const int ox = (int)(row % Wo);
+        const long long t = row / Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[u] = ld_raw16(x + (((long long)n * H + iy) * W + ix) * C + cv * V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long idx = base + u * stride;
+      if (idx < total) st_raw16(col + idx * V, v[u]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void im2col_scalar_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * 16 * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    int c = (int)(idx % C);
+    long long r = idx / C;
     int tap = (int)(r & 15);
     long long row = r >> 4;
     int ox = (int)(row % Wo);
@@ -21,81 +55,80 @@ __global__ void im2col_k4s2p1_kernel(const T* __restrict__ x, T* __restrict__ co
     int oy = (int)(t % Ho);
     int n = (int)(t / Ho);
     int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
-    T* dst = col + (row * 16 + tap) * C + cv * V;
     bool ok = (iy >= 0 && iy < H && ix >= 0 && ix < W);
-    const T* src = x + (((long long)n * H + iy) * W + ix) * C + cv * V;
-    if (V == 4) {
-      f4 v = {{0.f, 0.f, 0.f, 0.f}};
-      if (ok) v = ld_f4<T>(src);
-      st_f4<T>(dst, v);
-    } else {
-      st_f<T>(dst, ok ? ld_f<T>(src) : 0.f);
-    }
+    st_f<T>(col + idx, ok ? ld_f<T>(x + (((long long)n * H + iy) * W + ix) * C + c) : 0.f);
   }
 }
 
 // ---- col2im (gather form): y [N,2Hi,2Wi,C] <- col [N*Hi*Wi, 16*C] (+ col2 of a shared source) ----
 template <typename T, int V>
-__global__ void col2im_k4s2p1_kernel(const T* __restrict__ col, const T* __restrict__ col2, const int* __restrict__ grp_src,
-                                     int imgs_per_group, T* __restrict__ y, int N, int Hi, int Wi, int C,
-                                     const float* __restrict__ bias, int accumulate) {
+__global__ void __launch_bounds__(256) col2im_k4s2p1_kernel(const T* __restrict__ col, const T* __restrict__ col2,
+                                                            const int* __restrict__ grp_src, int imgs_per_group, T* __restrict__ y,
+                                                            int N, int Hi, int Wi, int C, const float* __restrict__ bias, int accumulate) {
   const int Ho = Hi * 2, Wo = Wi * 2, CV = C / V;
   const long long total = (long long)N * Ho * Wo * CV;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    long long p = idx / CV;
-    int ox = (int)(p % Wo);
-    long long t = p / Wo;
-    int oy = (int)(t % Ho);
-    int n = (int)(t / Ho);
+    const int cv = (int)(idx % CV);
+    const long long p = idx / CV;
+    const int ox = (int)(p % Wo);
+    const long long t = p / Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
     int n2 = 0;
     if (col2) n2 = grp_src[n / imgs_per_group] * imgs_per_group + (n % imgs_per_group);
     float acc[V];
 #pragma unroll
     for (int j = 0; j < V; j++) acc[j] = bias ? bias[cv * V + j] : 0.f;
     const int kh0 = (oy + 1) & 1, kw0 = (ox + 1) & 1;
+    // gather the (up to) 2x2 contributing taps; issue all loads first
+    uint4 raw[8];
+    bool on[4];
 #pragma unroll
     for (int a = 0; a < 2; a++) {
-      int kh = kh0 + 2 * a;
-      int iy = (oy + 1 - kh) >> 1;  // exact: oy+1-kh is even
-      if (oy + 1 - kh < 0 || iy >= Hi) continue;
 #pragma unroll
       for (int b = 0; b < 2; b++) {
-        int kw = kw0 + 2 * b;
-        int ix = (ox + 1 - kw) >> 1;
-        if (ox + 1 - kw < 0 || ix >= Wi) continue;
-        long long off = ((((long long)n * Hi + iy) * Wi + ix) * 16 + kh * 4 + kw) * C + cv * V;
-        if (V == 4) {
-          f4 v = ld_f4<T>(col + off);
-#pragma unroll
-          for (int j = 0; j < V; j++) acc[j] += v.v[j];
+        const int kh = kh0 + 2 * a, kw = kw0 + 2 * b;
+        const int ty = oy + 1 - kh, tx = ox + 1 - kw;
+        const int iy = ty >> 1, ix = tx >> 1;
+        const bool ok = (ty >= 0) && (iy < Hi) && (tx >= 0) && (ix < Wi);
+        on[a * 2 + b] = ok;
+        if (V > 1) {
+          raw[a * 2 + b] = make_uint4(0u, 0u, 0u, 0u);
+          raw[4 + a * 2 + b] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (!ok) continue;
+        const long long off = ((((long long)n * Hi + iy) * Wi + ix) * 16 + kh * 4 + kw) * C + cv * V;
+        if (V > 1) {
+          raw[a * 2 + b] = ld_raw16(col + off);
+          if (col2) raw[4 + a * 2 + b] = ld_raw16(col2 + ((((long long)n2 * Hi + iy) * Wi + ix) * 16 + kh * 4 + kw) * C + cv * V);
         } else {
           acc[0] += ld_f<T>(col + off);
-        }
-        if (col2) {
-          long long off2 = ((((long long)n2 * Hi + iy) * Wi + ix) * 16 + kh * 4 + kw) * C + cv * V;
-          if (V == 4) {
-            f4 v = ld_f4<T>(col2 + off2);
-#pragma unroll
-            for (int j = 0; j < V; j++) acc[j] += v.v[j];
-          } else {
-            acc[0] += ld_f<T>(col2 + off2);
-          }
+          if (col2) acc[0] += ld_f<T>(col2 + ((((long long)n2 * Hi + iy) * Wi + ix) * 16 + kh * 4 + kw) * C + cv * V);
         }
       }
     }
     T* dst = y + p * C + cv * V;
-    if (V == 4) {
-      f4 o;
-      if (accumulate) {
-        o = ld_f4<T>(dst);
+    if (V > 1) {
 #pragma unroll
-        for (int j = 0; j < V; j++) o.v[j] += acc[j];
-      } else {
+      for (int q = 0; q < 4; q++) {
+        if (!on[q]) continue;
+        float f[V > 1 ? V : 8];
+        unpack16<T>(raw[q], f);
 #pragma unroll
-        for (int j = 0; j < V; j++) o.v[j] = acc[j];
+        for (int j = 0; j < V; j++) acc[j] += f[j];
+        if (col2) {
+          unpack16<T>(raw[4 + q], f);
+#pragma unroll
+          for (int j = 0; j < V; j++) acc[j] += f[j];
+        }
       }
-      st_f4<T>(dst, o);
+      if (accumulate) {
+        float f[V > 1 ? V : 8];
+        unpack16<T>(ld_raw16(dst), f);
+#pragma unroll
+        for (int j = 0; j < V; j++) acc[j] += f[j];
+      }
+      st_raw16(dst, pack16<T>(acc));
     } else {
       st_f<T>(dst, accumulate ? ld_f<T>(dst) + acc[0] : acc[0]);
     }
@@ -154,7 +187,7 @@ __global__ void group_sum_kernel(const T* __restrict__ in, T* __restrict__ out, 
 
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
-  const long long cap = 148LL * 32;
+  const long long cap = 148LL * 64;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -163,12 +196,14 @@ inline int grid_for(long long total, int block) {
 int p2pvg_im2col_k4s2p1_impl(const void* x, void* col, int dtype, int N, int H, int W, int C, cudaStream_t st) {
   P2PVG_REQUIRE((H % 2 == 0) && (W % 2 == 0), P2PVG_ERR_BAD_ARG, "im2col: odd spatial size %dx%d", H, W);
   if (N == 0) return P2PVG_OK;
-  if (C % 4 == 0) {
-    long long total = (long long)N * (H / 2) * (W / 2) * 16 * (C / 4);
-    DISPATCH_DTYPE(dtype, T, (im2col_k4s2p1_kernel<T, 4><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
+  const int vec = (dtype == P2PVG_BF16) ? 8 : 4;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(col)) & 15) == 0;
+  if (C % vec == 0 && aligned) {
+    long long total = (long long)N * (H / 2) * (W / 2) * 16 * (C / vec);
+    DISPATCH_DTYPE(dtype, T, (im2col_vec_kernel<T><<<grid_for((total + 3) / 4, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
   } else {
     long long total = (long long)N * (H / 2) * (W / 2) * 16 * C;
-    DISPATCH_DTYPE(dtype, T, (im2col_k4s2p1_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
+    DISPATCH_DTYPE(dtype, T, (im2col_scalar_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
   }
   return p2pvg_check_launch("im2col_k4s2p1");
 }
@@ -177,10 +212,16 @@ int p2pvg_col2im_k4s2p1_impl(const void* col, const void* col2, const int* grp_s
                              int N, int Hi, int Wi, int C, const float* bias, int accumulate, cudaStream_t st) {
   if (N == 0) return P2PVG_OK;
   P2PVG_REQUIRE(col2 == nullptr || (grp_src != nullptr && imgs_per_group > 0), P2PVG_ERR_BAD_ARG, "col2im: col2 needs grp_src");
-  if (C % 4 == 0) {
-    long long total = (long long)N * Hi * 2 * Wi * 2 * (C / 4);
-    DISPATCH_DTYPE(dtype, T, (col2im_k4s2p1_kernel<T, 4><<<grid_for(total, 256), 256, 0, st>>>(
-                                 (const T*)col, (const T*)col2, grp_src, imgs_per_group, (T*)y, N, Hi, Wi, C, bias, accumulate)));
+  const int vec = (dtype == P2PVG_BF16) ? 8 : 4;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(col2) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (C % vec == 0 && aligned) {
+    long long total = (long long)N * Hi * 2 * Wi * 2 * (C / vec);
+    if (dtype == P2PVG_BF16)
+      col2im_k4s2p1_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)col, (const bf16*)col2, grp_src, imgs_per_group,
+                                                                          (bf16*)y, N, Hi, Wi, C, bias, accumulate);
+    else
+      col2im_k4s2p1_kernel<float, 4><<<grid_for(total, 256), 256, 0, st>>>((const float*)col, (const float*)col2, grp_src,
+                                                                           imgs_per_group, (float*)y, N, Hi, Wi, C, bias, accumulate);
   } else {
     long long total = (long long)N * Hi * 2 * Wi * 2 * C;
     DISPATCH_DTYPE(dtype, T, (col2im_k4s2p1_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>(
