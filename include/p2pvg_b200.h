@@ -35,6 +35,7 @@ extern "C" {
 #define P2PVG_ACT_NONE 0
 #define P2PVG_ACT_LRELU 1 /* LeakyReLU(0.2): models/dcgan_64.py:10,22 */
 #define P2PVG_ACT_TANH 2  /* models/dcgan_64.py:45, models/lstm.py:18 */
+#define P2PVG_ACT_SIGMOID 3 /* models/dcgan_64.py:77 (stand-alone decoder forward; act_fwd only) */
 
 int p2pvg_version(void);
 const char* p2pvg_last_error(void);
@@ -81,6 +82,9 @@ int p2pvg_bn_act(const void* x, void* y, int dtype, const float* scale, const fl
 int p2pvg_bn_bwd(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
                  const float* gamma, int G, int64_t R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
                  float* sum_dzx, void* stream);
+/* eval-mode BatchNorm (running statistics; generate.py / p2p_generate): scale = gamma/sqrt(rvar+eps), shift = beta-rmean*scale */
+int p2pvg_bn_eval_coeffs(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, int C,
+                         float* scale, float* shift, void* stream);
 int p2pvg_bn_param_grad(const float* sum_dz, const float* sum_dzx, int G, int C, float* dgamma, float* dbeta, void* stream);
 /* running_mean / running_var EMA applied call by call in the reference's call order. */
 int p2pvg_bn_ema(float* rmean, float* rvar, const float* mean, const float* var_unbiased, const int* order, int ncalls, int C,

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libp2pvg_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 
 _lib = None
 
@@ -154,6 +154,10 @@ class CudaKernels:
 
     def bn_param_grad(self, sum_dz, sum_dzx, G, C, dgamma, dbeta):
         self._ck(self.lib.p2pvg_bn_param_grad(_p(sum_dz), _p(sum_dzx), _i(G), _i(C), _p(dgamma), _p(dbeta), self._stream()))
+
+    def bn_eval_coeffs(self, gamma, beta, rmean, rvar, C, scale, shift, eps=1e-5):
+        self._ck(self.lib.p2pvg_bn_eval_coeffs(_p(gamma), _p(beta), _p(rmean), _p(rvar), _f(eps), _i(C), _p(scale), _p(shift),
+                                               self._stream()))
 
     def bn_ema(self, rmean, rvar, mean, var_unb, order, ncalls, C, momentum=0.1):
         self._ck(self.lib.p2pvg_bn_ema(_p(rmean), _p(rvar), _p(mean), _p(var_unb), _p(order), _i(ncalls), _i(C), _f(momentum),

@@ -208,6 +208,15 @@ __global__ void bn_param_grad_kernel(const float* __restrict__ sum_dz, const flo
   dbeta[c] = b;
 }
 
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rmean,
+                                      const float* __restrict__ rvar, float eps, int C, float* __restrict__ scale, float* __restrict__ shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = gamma[c] / sqrtf(rvar[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - rmean[c] * sc;
+}
+
 __global__ void bn_ema_kernel(float* __restrict__ rmean, float* __restrict__ rvar, const float* __restrict__ mean,
                               const float* __restrict__ var_unbiased, const int* __restrict__ order, int ncalls, int C,
                               float momentum) {
@@ -308,4 +317,10 @@ int p2pvg_bn_ema_impl(float* rmean, float* rvar, const float* mean, const float*
                       float momentum, cudaStream_t st) {
   bn_ema_kernel<<<cdiv(C, 128), 128, 0, st>>>(rmean, rvar, mean, var_unbiased, order, ncalls, C, momentum);
   return p2pvg_check_launch("bn_ema");
+}
+
+int p2pvg_bn_eval_coeffs_impl(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, int C, float* scale,
+                              float* shift, cudaStream_t st) {
+  bn_eval_coeffs_kernel<<<cdiv(C, 128), 128, 0, st>>>(gamma, beta, rmean, rvar, eps, C, scale, shift);
+  return p2pvg_check_launch("bn_eval_coeffs");
 }

@@ -193,6 +193,7 @@ __global__ void act_fwd_kernel(float* __restrict__ x, long long n, int act) {
     float v = x[i];
     if (act == P2PVG_ACT_TANH) v = tanhf(v);
     else if (act == P2PVG_ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+    else if (act == P2PVG_ACT_SIGMOID) v = sigmoidf_(v);
     x[i] = v;
   }
 }
