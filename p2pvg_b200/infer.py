@@ -55,6 +55,7 @@ def _stages(mod):
 def encoder_forward(mod, x):
     K = kernels_for(x.device)
     dev, adt = x.device, _act_dtype()
+    K.set_fp32_gemm_mode(0)  # fp32 operands only occur in parity mode here: keep them exact
     chans = _stages(mod)
     n = len(chans)
     B, nc, H = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
@@ -108,6 +109,7 @@ def _to_nhwc(K, t, adt):
 def decoder_forward(mod, vec, skip):
     K = kernels_for(vec.device)
     dev, adt = vec.device, _act_dtype()
+    K.set_fp32_gemm_mode(0)
     chans = _stages(mod)
     n, g = len(chans), mod.dim
     vec = vec.reshape(-1, g).float().contiguous()
