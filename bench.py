@@ -169,7 +169,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.seq, args.batch
     os.environ["P2PVG_PRECISION"] = args.precision
-    os.environ["P2PVG_GRAPH"] = "0" if (args.no_graph or world > 1) else "1"
+    # multi-GPU: the NCCL all-reduces are captured into the step graph as well (P2PVG_DP_GRAPH=0 disables)
+    dp_graph = os.environ.get("P2PVG_DP_GRAPH", "1") != "0"
+    os.environ["P2PVG_GRAPH"] = "0" if (args.no_graph or (world > 1 and not dp_graph)) else "1"
     torch.manual_seed(1)
     np.random.seed(0)
     model = P2PModel(B, 1, 128, 10, 256, 1, 1, 2, opt=make_opt(dcgan_64, B)).cuda()
