@@ -57,6 +57,20 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
                int64_t ldc, int M, int N, int K, int accumulate, const float* bias, const void* addend, int64_t ldd,
                void* workspace, size_t ws_bytes, void* stream);
 
+/* Implicit-GEMM 4x4 / stride-2 / pad-1 convolution family on NHWC bf16 tensors (TMA 4-D pixel-box loads feeding tcgen05;
+ * no im2col / col2im buffers).  H, W = size of the SMALL map (the big map is 2H x 2W).
+ *   kind 0: c_small[N,H,W,Cn] = conv_s2(a_big[N,2H,2W,Ck]) . b[Cn,(kh,kw,Ck)] + bias       nn.Conv2d(.,.,4,2,1) forward
+ *           (models/dcgan_64.py:8) and the data-gradient of nn.ConvTranspose2d(.,.,4,2,1) (models/dcgan_64.py:20)
+ *   kind 1: c[Cm,(kh,kw,Cn)] = sum_pix a_small[pix,Cm]^T . gather_s2(b_big[N,2H,2W,Cn])    the weight gradients of both (fp32)
+ *   kind 2: c_big[N,2H,2W,Cn] = convT_s2(a_small[N,H,W,Ck]) . b[Ck,(kh,kw,Cn)] + bias + addend[src]   ConvTranspose2d forward
+ *           and the Conv2d data-gradient; `addend` (fp32, big-map layout) is the skip half of torch.cat([d, skip], 1)
+ *           (models/dcgan_64.py:84-87) computed once per distinct source call; image n adds addend image
+ *           grp_src[n / imgs_per_group] * imgs_per_group + n % imgs_per_group.
+ * Returns P2PVG_ERR_UNSUPPORTED for shapes outside the pixel-box tiling (channels not a multiple of 64, ...). */
+int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c, int c_dtype, int64_t ldc, int N, int H, int W, int Ck,
+                    int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
+                    void* workspace, size_t ws_bytes, void* stream);
+
 /* 4x4 / stride 2 / pad 1 lowering (nn.Conv2d(nin,nout,4,2,1), models/dcgan_64.py:8; and the data-gradient of
  * nn.ConvTranspose2d(nin,nout,4,2,1), models/dcgan_64.py:20): x [N,H,W,C] -> col [N*H/2*W/2, 16*C], K order (kh,kw,c). */
 int p2pvg_im2col_k4s2p1(const void* x, void* col, int dtype, int N, int H, int W, int C, void* stream);

@@ -118,6 +118,19 @@ class CudaKernels:
                                      _i(_dt(C)), _i64(ldc), _i(M), _i(N), _i(K), _i(int(accumulate)), _p(bias), _p(addend),
                                      _i64(ldd), _p(ws), _sz(ws.numel() if ws is not None else 0), self._stream()))
 
+    # -- implicit-GEMM convolutions ---------------------------------------------------------
+    def conv_gemm(self, kind, a, b, c, N, H, W, Ck, Cn, Cm=0, ldb=None, ldc=None, bias=None, addend=None, grp_src=None,
+                  imgs_per_group=0, accumulate=False):
+        """kind 0/1/2 of p2pvg_conv_gemm (see include/p2pvg_b200.h).  H, W: small-map size."""
+        if ldb is None:
+            ldb = 16 * Ck if kind == 0 else 16 * Cn
+        if ldc is None:
+            ldc = 16 * Cn if kind == 1 else Cn
+        ws = self.gemm_workspace()
+        self._ck(self.lib.p2pvg_conv_gemm(_i(kind), _p(a), _p(b), _i64(ldb), _p(c), _i(_dt(c)), _i64(ldc), _i(N), _i(H), _i(W), _i(Ck),
+                                          _i(Cn), _i(Cm), _p(bias), _p(addend), _p(grp_src), _i(imgs_per_group), _i(int(accumulate)),
+                                          _p(ws), _sz(ws.numel()), self._stream()))
+
     # -- conv lowering ---------------------------------------------------------------------
     def im2col(self, x, col, N, H, W, C):
         self._ck(self.lib.p2pvg_im2col_k4s2p1(_p(x), _p(col), _i(_dt(x)), _i(N), _i(H), _i(W), _i(C), self._stream()))

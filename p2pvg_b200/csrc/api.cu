@@ -33,6 +33,8 @@ int p2pvg_gemm_tf32(const void*, long long, const void*, long long, void*, int, 
 int p2pvg_gemm_tc(const void*, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int, const float*,
                   const void*, long long, void*, size_t, cudaStream_t);
 int p2pvg_gemm_tc_available();
+int p2pvg_conv_gemm_impl(int, const void*, const void*, long long, void*, int, long long, int, int, int, int, int, int, const float*,
+                         const float*, const int*, int, int, void*, size_t, cudaStream_t);
 int p2pvg_im2col_k4s2p1_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
 int p2pvg_col2im_k4s2p1_impl(const void*, const void*, const int*, int, void*, int, int, int, int, int, const float*, int, cudaStream_t);
 int p2pvg_permute4_impl(const void*, int, void*, int, const int*, const long long*, int, cudaStream_t);
@@ -106,6 +108,14 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
   }
   return p2pvg_gemm_simt(A, in_dtype, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace,
                          ws_bytes, ST);
+}
+
+int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c, int c_dtype, int64_t ldc, int N, int H, int W, int Ck,
+                    int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
+                    void* workspace, size_t ws_bytes, void* stream) {
+  P2PVG_REQUIRE(a && b && c, P2PVG_ERR_BAD_ARG, "conv_gemm: null operand");
+  return p2pvg_conv_gemm_impl(kind, a, b, ldb, c, c_dtype, ldc, N, H, W, Ck, Cn, Cm, bias, addend, grp_src, imgs_per_group, accumulate,
+                              workspace, ws_bytes, ST);
 }
 
 int p2pvg_im2col_k4s2p1(const void* x, void* col, int dtype, int N, int H, int W, int C, void* stream) {

@@ -1,0 +1,459 @@
+// Implicit-GEMM 4x4 / stride-2 / pad-1 convolution family on NHWC bf16 tensors (no im2col / col2im buffers).
+// Same persistent tcgen05 skeleton as gemm_tc.cu (TMA -> 128B-swizzled smem -> tcgen05.mma kind::f16 -> TMEM ->
+// tcgen05.ld epilogue, double-buffered accumulator); what changes is how an operand tile is fetched:
+//
+//   "pixel box" tiles: P consecutive NHW pixels of the SMALL map (H x W per image) are a rectangular box
+//   {bw = W, bh, bn}; the operand rows for filter tap (kh,kw) are the BIG-map pixels (2y+kh-1, 2x+kw-1), i.e. one
+//   4-D TMA load with elementStrides {1,2,2,1} whose out-of-bounds part (the conv padding) is zero-filled by the
+//   hardware.  For the transposed direction the rows are SMALL-map pixels (y+dy, x+dx): a stride-1 4-D box.
+//
+// kind 0  y_small[N,H,W,Cn] = conv_s2(x_big[N,2H,2W,Ck]) . W[Cn, (tap, Ck)]           Conv forward, ConvT data-gradient
+// kind 1  g[Cm, (tap, Cn)]  = sum_pix a_small[pix, Cm]^T . gather_s2(b_big)[pix, tap, Cn]   weight gradients (split-K)
+// kind 2  y_big[N,2H,2W,Cn] = convT_s2(x_small[N,H,W,Ck]) . W[Ck, (tap, Cn)] + bias + addend   ConvT forward, Conv data-gradient
+//         (4 output-parity phases, each a 2x2 stride-1 convolution; `addend` holds the skip-connection half of
+//          torch.cat([d, skip]) computed once per distinct source call and is indexed through grp_src)
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * 128;
+
+template <int BN> struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+};
+
+struct Geom {
+  int N, H, W;          // images, small-map height / width
+  int Ck, Cn;           // reduction channels / output channels (kind 0,2);  kind 1: Cm = M extent, Cn = gathered channels
+  int M;                // GEMM M: kind 0/2: N*H*W pixels; kind 1: Cm
+  int Ntot;             // GEMM N: kind 0/2: Cn; kind 1: 16*Cn
+  int bh128, bn128;     // pixel box of 128 pixels: {W, bh128, bn128}
+  int bh64, bn64;       // pixel box of 64 pixels (kind 1 K-blocks)
+  int imgs_per_group;   // kind 2 addend indexing
+};
+
+__device__ __forceinline__ void pix_block(int pb, int P, int H, int W, int bh, int bn, int& n0, int& y0) {
+  const int HW = H * W;
+  if (HW >= P) {
+    const int bpi = HW / P;
+    n0 = pb / bpi;
+    y0 = (pb - n0 * bpi) * bh;
+  } else {
+    n0 = pb * bn;
+    y0 = 0;
+  }
+}
+
+template <int KIND, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv, int c_bf16,
+                 long long ldc, Geom g, int accumulate, const float* __restrict__ bias, const float* __restrict__ addend,
+                 const int* __restrict__ grp_src, float* __restrict__ partial, int kb_per_split, int splits) {
+  using C_ = Cfg<BN>;
+  constexpr bool A_MN = (KIND == 1), B_MN = (KIND != 0);
+  constexpr int UMMA_K = 16;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C_::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C_::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (g.Ntot + BN - 1) / BN;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int phases = (KIND == 2) ? 4 : 1;
+  const int num_tiles = tiles_mn * splits * phases;
+  const int cchunks = g.Ck / 64;
+  // K blocks: kind 0: 16 taps x Ck/64; kind 2: 4 taps x Ck/64; kind 1: pixel blocks of 64
+  const int nkb_total = (KIND == 0) ? 16 * cchunks : (KIND == 2) ? 4 * cchunks : (g.N * g.H * g.W + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C_::STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int ph = t / (tiles_mn * splits);           // output-parity phase (kind 2)
+        const int t2 = t - ph * tiles_mn * splits;
+        const int z = t2 / tiles_mn, r = t2 - z * tiles_mn;
+        const int mt = r / tiles_n, nt = r % tiles_n;
+        const int n0 = nt * BN;
+        const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
+        int pn0 = 0, py0 = 0;
+        if (KIND != 1) pix_block(mt, 128, g.H, g.W, g.bh128, g.bn128, pn0, py0);
+        const int pa = ph >> 1, pb_ = ph & 1;
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          const int s = it % C_::STAGES;
+          const uint32_t par = (it / C_::STAGES) & 1;
+          mbar_wait(&empty_bar[s], par ^ 1);
+          uint8_t* sa = smem + s * C_::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
+          if (KIND == 0) {
+            const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * 64;
+            tma_load_4d(&tmA, &full_bar[s], sa, c0, (tap & 3) - 1, 2 * py0 + (tap >> 2) - 1, pn0);
+            tma_load_2d(&tmB, &full_bar[s], sb, tap * g.Ck + c0, n0);
+          } else if (KIND == 2) {
+            const int tq = kb / cchunks, c0 = (kb - tq * cchunks) * 64;
+            const int i = tq >> 1, j = tq & 1;
+            // phase a: taps (dy=0, ky=a+1) and (dy = a ? +1 : -1, ky = a ? 0 : 3); same along x
+            const int dy = i == 0 ? 0 : (pa ? 1 : -1), ky = i == 0 ? pa + 1 : (pa ? 0 : 3);
+            const int dx = j == 0 ? 0 : (pb_ ? 1 : -1), kx = j == 0 ? pb_ + 1 : (pb_ ? 0 : 3);
+            tma_load_4d(&tmA, &full_bar[s], sa, c0, dx, py0 + dy, pn0);
+#pragma unroll
+            for (int q = 0; q < BN / 64; q++)
+              tma_load_2d(&tmB, &full_bar[s], sb + q * 64 * 128, (ky * 4 + kx) * g.Cn + n0 + 64 * q, c0);
+          } else {
+            int kn0, ky0;
+            pix_block(kb, 64, g.H, g.W, g.bh64, g.bn64, kn0, ky0);
+            const int m0 = mt * BLOCK_M;
+            tma_load_2d(&tmA, &full_bar[s], sa, m0, kb * 64);
+            tma_load_2d(&tmA, &full_bar[s], sa + 64 * 128, m0 + 64, kb * 64);
+#pragma unroll
+            for (int q = 0; q < BN / 64; q++) {
+              const int nb = n0 + 64 * q;
+              const int tap = nb / g.Cn, c0 = nb - tap * g.Cn;
+              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, c0, (tap & 3) - 1, 2 * ky0 + (tap >> 2) - 1, kn0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
+        const int ph = t / (tiles_mn * splits);
+        const int t2 = t - ph * tiles_mn * splits;
+        const int z = t2 / tiles_mn;
+        const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
+        const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          const int s = it % C_::STAGES;
+          const uint32_t par = (it / C_::STAGES) & 1;
+          mbar_wait(&full_bar[s], par);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 64 / UMMA_K; k++) {
+            const uint64_t da = A_MN ? make_desc(sa + k * UMMA_K * 128, 64 * 128, 1024) : make_desc(sa + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_desc(sb + k * UMMA_K * 128, 64 * 128, 1024) : make_desc(sb + k * 32, 0, 1024);
+            umma_bf16(tmem_c, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
+      const int ph = t / (tiles_mn * splits);
+      const int t2 = t - ph * tiles_mn * splits;
+      const int z = t2 / tiles_mn, r = t2 - z * tiles_mn;
+      const int mt = r / tiles_n, nt = r % tiles_n;
+      const int n0 = nt * BN;
+      const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
+      const int rt = q * 32 + lane;  // row within the tile
+      long long out_row = (long long)mt * BLOCK_M + rt;
+      long long add_row = 0;
+      bool row_ok = out_row < g.M;
+      if (KIND == 2) {
+        // tile row -> small-map pixel -> big-map output pixel of this parity phase
+        int pn0, py0;
+        pix_block(mt, 128, g.H, g.W, g.bh128, g.bn128, pn0, py0);
+        const int HW = g.H * g.W;
+        int nn, yy, xx;
+        if (HW >= 128) { nn = 0; yy = rt / g.W; xx = rt - yy * g.W; }
+        else { nn = rt / HW; const int rem = rt - nn * HW; yy = rem / g.W; xx = rem - yy * g.W; }
+        const int n = pn0 + nn, y = py0 + yy;
+        row_ok = (n < g.N) && (y < g.H);
+        const int oy = 2 * y + (ph >> 1), ox = 2 * xx + (ph & 1);
+        out_row = ((long long)n * (2 * g.H) + oy) * (2 * g.W) + ox;
+        if (addend && row_ok) {
+          const int n2 = grp_src[n / g.imgs_per_group] * g.imgs_per_group + (n % g.imgs_per_group);
+          add_row = ((long long)n2 * (2 * g.H) + oy) * (2 * g.W) + ox;
+        }
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        const int nbase = n0 + c * 32;
+        if (!row_ok || nbase >= g.Ntot) continue;
+        if (KIND == 1 && partial != nullptr) {
+          float* dst = partial + ((long long)z * g.M + out_row) * g.Ntot + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          continue;
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] += bias[nbase + j];
+        }
+        if (KIND == 2 && addend) {
+          const float* ar = addend + add_row * g.Ntot + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(ar + j);
+            f[j] += a4.x; f[j + 1] += a4.y; f[j + 2] += a4.z; f[j + 3] += a4.w;
+          }
+        }
+        if (c_bf16) {
+          bf16* crow = reinterpret_cast<bf16*>(Cv) + out_row * ldc + nbase;
+          if (accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) f[j] += __bfloat162float(crow[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(crow + j) = pk;
+          }
+        } else {
+          float* crow = reinterpret_cast<float*>(Cv) + out_row * ldc + nbase;
+          if (accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) f[j] += crow[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+__global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ C, long long ldc, int M, int N,
+                                          int accumulate) {
+  const long long total = (long long)M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / N;
+    const int n = (int)(idx - m * N);
+    float acc = 0.f;
+    for (int z = 0; z < splits; z++) acc += partial[(long long)z * total + idx];
+    if (accumulate) acc += C[m * ldc + n];
+    C[m * ldc + n] = acc;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_enc = nullptr;
+std::once_flag g_once2;
+int g_sms = 148;
+int g_attr[3][2] = {};
+
+void resolve2() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_sms = sms;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    g_enc = reinterpret_cast<EncodeTiledFn>(fn);
+  (void)cudaGetLastError();
+}
+
+int map2d(CUtensorMap* m, const void* base, long long dim0, long long dim1, long long ld, int box1) {
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    p2pvg_set_error("conv_gemm: 2-D tensor map failed (%d)", (int)r);
+    return P2PVG_ERR_CUDA;
+  }
+  return P2PVG_OK;
+}
+
+// NHWC [N, Hm, Wm, C] pixel-box map: box {64 ch, bw*s, bh*s, bn} traversed with stride s in x and y
+int map4d(CUtensorMap* m, const void* base, int N, int Hm, int Wm, int C, int bw, int bh, int bn, int s) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wm, (cuuint64_t)Hm, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wm * C * 2, (cuuint64_t)Hm * Wm * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * s), (cuuint32_t)(bh * s), (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+  CUresult r = g_enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    p2pvg_set_error("conv_gemm: 4-D tensor map failed (%d): N=%d H=%d W=%d C=%d box=(%d,%d,%d) s=%d", (int)r, N, Hm, Wm, C, bw, bh, bn, s);
+    return P2PVG_ERR_CUDA;
+  }
+  return P2PVG_OK;
+}
+
+bool box_for(int P, int H, int W, int& bh, int& bn) {
+  const int HW = H * W;
+  if (HW >= P) {
+    if (P % W != 0 || (H % (P / W)) != 0) return false;
+    bh = P / W;
+    bn = 1;
+  } else {
+    if (P % HW != 0) return false;
+    bh = H;
+    bn = P / HW;
+  }
+  return bh * 2 <= 256 && W * 2 <= 256 && bn <= 256;
+}
+
+template <int KIND, int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, const Geom& g, int accumulate,
+           const float* bias, const float* addend, const int* grp_src, float* partial, int splits, int kb_per_split, cudaStream_t st) {
+  auto kern = conv_gemm_kernel<KIND, BN>;
+  int& done = g_attr[KIND][BN == 128];
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      p2pvg_set_error("conv_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return P2PVG_ERR_CUDA;
+    }
+    done = 1;
+  }
+  long long tiles = (long long)cdiv(g.M, BLOCK_M) * cdiv(g.Ntot, BN) * splits * (KIND == 2 ? 4 : 1);
+  int grid = (int)(tiles < g_sms ? tiles : g_sms);
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, C, c_dtype == P2PVG_BF16, ldc, g, accumulate, bias, addend, grp_src, partial,
+                                                      kb_per_split, splits);
+  return p2pvg_check_launch("conv_gemm");
+}
+
+}  // namespace
+
+// a, b: see the kind table at the top.  H, W: SMALL-map size.  Returns P2PVG_ERR_UNSUPPORTED when the shape does not
+// fit the pixel-box tiling (the caller then uses the explicit im2col / col2im path).
+int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, void* c, int c_dtype, long long ldc, int N, int H, int W,
+                         int Ck, int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group,
+                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  std::call_once(g_once2, resolve2);
+  P2PVG_REQUIRE(g_enc != nullptr, P2PVG_ERR_UNSUPPORTED, "conv_gemm: cuTensorMapEncodeTiled unavailable");
+  P2PVG_REQUIRE(kind >= 0 && kind <= 2, P2PVG_ERR_BAD_ARG, "conv_gemm: bad kind %d", kind);
+  if (N <= 0) return P2PVG_OK;
+  Geom g;
+  g.N = N; g.H = H; g.W = W; g.Ck = Ck; g.Cn = Cn; g.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : 1;
+  bool ok = box_for(128, H, W, g.bh128, g.bn128) && box_for(64, H, W, g.bh64, g.bn64);
+  ok = ok && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+  if (kind == 1) ok = ok && (Cn % 64 == 0) && (Cm % 8 == 0);
+  else ok = ok && (Ck % 64 == 0) && (Cn % 32 == 0) && (ldb % 8 == 0);
+  if (kind == 2) ok = ok && (Cn % 64 == 0);
+  if (!ok) {
+    p2pvg_set_error("conv_gemm: shape not supported by the pixel-box tiling (kind=%d N=%d H=%d W=%d Ck=%d Cn=%d)", kind, N, H, W, Ck, Cn);
+    return P2PVG_ERR_UNSUPPORTED;
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  const long long pix = (long long)N * H * W;
+  if (kind == 0) {
+    g.M = (int)pix; g.Ntot = Cn;
+    rc = map4d(&ta, a, N, 2 * H, 2 * W, Ck, W, g.bh128, g.bn128, 2);
+    if (rc) return rc;
+    const int BN = Cn > 64 ? 128 : 64;
+    rc = map2d(&tb, b, 16LL * Ck, Cn, ldb, BN);
+    if (rc) return rc;
+    const int nkb = 16 * (Ck / 64);
+    if (BN == 128) return launch<0, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, nullptr, nullptr, nullptr, 1, nkb, st);
+    return launch<0, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, nullptr, nullptr, nullptr, 1, nkb, st);
+  }
+  if (kind == 2) {
+    g.M = (int)pix; g.Ntot = Cn;
+    rc = map4d(&ta, a, N, H, W, Ck, W, g.bh128, g.bn128, 1);
+    if (rc) return rc;
+    rc = map2d(&tb, b, 16LL * Cn, Ck, ldb, 64);  // MN-major weight [Ck rows][16*Cn]
+    if (rc) return rc;
+    const int nkb = 4 * (Ck / 64);
+    const int BN = Cn > 64 ? 128 : 64;
+    if (BN == 128) return launch<2, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
+    return launch<2, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
+  }
+  // kind 1: weight gradient
+  P2PVG_REQUIRE(c_dtype == P2PVG_F32, P2PVG_ERR_BAD_ARG, "conv_gemm kind 1 writes fp32");
+  g.M = Cm; g.Ntot = 16 * Cn; g.Ck = 64;
+  rc = map2d(&ta, a, Cm, pix, Cm, 64);  // a_small [pix][Cm] as MN-major A
+  if (rc) return rc;
+  rc = map4d(&tb, b, N, 2 * H, 2 * W, Cn, W, g.bh64, g.bn64, 2);
+  if (rc) return rc;
+  const int BN = Cn >= 128 ? 128 : 64;
+  const int nkb = (int)((pix + 63) / 64);
+  const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(16 * Cn, BN);
+  int splits = 1;
+  if (tiles < 120 && nkb >= 16) {
+    long long want = (2 * g_sms + tiles - 1) / tiles, maxs = nkb / 8;
+    splits = (int)(want < maxs ? want : maxs);
+    if (splits < 1) splits = 1;
+    while (splits > 1 && (ws == nullptr || (size_t)splits * Cm * 16 * Cn * sizeof(float) > ws_bytes)) splits /= 2;
+  }
+  int kbps = cdiv(nkb, splits);
+  splits = cdiv(nkb, kbps);
+  float* partial = splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
+  if (BN == 128) rc = launch<1, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
+  else rc = launch<1, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
+  if (rc) return rc;
+  if (splits > 1) {
+    long long total = (long long)Cm * 16 * Cn;
+    int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, (float*)c, ldc, Cm, 16 * Cn, accumulate);
+    return p2pvg_check_launch("conv_splitk_reduce");
+  }
+  return P2PVG_OK;
+}
