@@ -144,6 +144,10 @@ class TrainEngine:
         self.dist = None  # (torch.distributed, group, world_size) when batch-sharded over several GPUs
         # bf16 mode: the fp32 LSTM GEMMs run on the tensor cores at TF32 precision; fp32 mode stays exact
         self.tc_lstm = (act_dtype == torch.bfloat16) and hasattr(kernels, "set_fp32_gemm_mode")
+        # bf16 mode: 4x4/s2 (transposed) convolutions with >= 64 channels on both sides run as implicit GEMMs (4-D TMA
+        # pixel-box gathers), without im2col / col2im buffers; P2PVG_IMPLICIT=0 keeps the explicit lowering
+        import os
+        self.implicit = (act_dtype == torch.bfloat16) and hasattr(kernels, "conv_gemm") and os.environ.get("P2PVG_IMPLICIT", "1") != "0"
         self.last_plan = None
 
     # ------------------------------------------------------------------ memory
@@ -349,14 +353,19 @@ class TrainEngine:
             cout = self.chans[l]
             Ho = H // 2
             M = N * Ho * Ho
-            col = self.buf(f"enc_col{l}", M * 16 * cin)
             raw = self.buf(f"enc_raw{l}", M * cout)
             y = self.buf(f"enc_y{l}", M * cout)
             cn, bn = self.enc_names(l)
-            K.im2col(a, col, N, H, H, cin)
-            K.gemm(col, self._packed[f"enc{l}"], raw, M, cout, 16 * cin, bias=P[cn + ".bias"])
+            imp = self.implicit and cin % 64 == 0 and cout % 64 == 0
+            col = None
+            if imp:
+                K.conv_gemm(0, a, self._packed[f"enc{l}"], raw, N, Ho, Ho, cin, cout, bias=P[cn + ".bias"])
+            else:
+                col = self.buf(f"enc_col{l}", M * 16 * cin)
+                K.im2col(a, col, N, H, H, cin)
+                K.gemm(col, self._packed[f"enc{l}"], raw, M, cout, 16 * cin, bias=P[cn + ".bias"])
             st = self.bn_forward("enc", l, raw, y, T, B * Ho * Ho, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
-            self.enc.append(dict(col=col, raw=raw, y=y, st=st, cin=cin, cout=cout, Hin=H, Hout=Ho, M=M))
+            self.enc.append(dict(col=col, raw=raw, y=y, st=st, cin=cin, cout=cout, Hin=H, Hout=Ho, M=M, imp=imp, inp=a))
             a, H = y, Ho
         # final 4x4 valid conv == GEMM over the flattened 4x4xC map
         ctop = self.chans[-1]
@@ -504,15 +513,22 @@ class TrainEngine:
             Md, Ms = N * Hi * Hi, nskip * B * Hi * Hi
             wp = self._packed[f"dec{k}"]
             wD, wS = wp[:cd * 16 * cout], wp[cd * 16 * cout:]
-            colD = self.buf("dec_colD", Md * 16 * cout)
-            colS = self.buf("dec_colS", Ms * 16 * cout)
-            K.gemm(d, wD, colD, Md, 16 * cout, cd, b_mn=True)
-            K.gemm(skip, wS, colS, Ms, 16 * cout, cd, b_mn=True)
             cn, bn = self.dec_names(k)
             Mo = N * 4 * Hi * Hi
             raw = self.buf(f"dec_raw{k}", Mo * cout)
-            K.col2im(colD, raw, N, Hi, Hi, cout, bias=P[cn + ".bias"], col2=colS, grp_src=self.ix["skip_src"], imgs_per_group=B)
-            rec = dict(inp=d, skip=skip, raw=raw, cd=cd, cout=cout, Hi=Hi, Md=Md, Ms=Ms)
+            imp = self.implicit and cd % 64 == 0 and cout % 64 == 0
+            if imp:
+                # skip half once per distinct source frame (fp32, bias folded in), added in the epilogue of the main GEMM
+                addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
+                K.conv_gemm(2, skip, wS, addS, nskip * B, Hi, Hi, cd, cout, bias=P[cn + ".bias"])
+                K.conv_gemm(2, d, wD, raw, N, Hi, Hi, cd, cout, addend=addS, grp_src=self.ix["skip_src"], imgs_per_group=B)
+            else:
+                colD = self.buf("dec_colD", Md * 16 * cout)
+                colS = self.buf("dec_colS", Ms * 16 * cout)
+                K.gemm(d, wD, colD, Md, 16 * cout, cd, b_mn=True)
+                K.gemm(skip, wS, colS, Ms, 16 * cout, cd, b_mn=True)
+                K.col2im(colD, raw, N, Hi, Hi, cout, bias=P[cn + ".bias"], col2=colS, grp_src=self.ix["skip_src"], imgs_per_group=B)
+            rec = dict(inp=d, skip=skip, raw=raw, cd=cd, cout=cout, Hi=Hi, Md=Md, Ms=Ms, imp=imp)
             if k < n - 1:
                 dn = self.buf(f"dec_d{k}", Mo * cout)
                 rec["st"] = self.bn_forward("dec", k, raw, dn, G, B * 4 * Hi * Hi, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
@@ -567,24 +583,40 @@ class TrainEngine:
                     K.bn_param_grad(st["sdz"][c0:c1], st["sdzx"][c0:c1], Gn, cout, A.g[bn + ".weight"], A.g[bn + ".bias"])
             if want_wgrad:
                 K.colsum(dy, rows_o, cout, cout, A.g[cn + ".bias"])
-            dcol = self.buf("scratch_dcol", Md * 16 * cout)
-            K.im2col(dy, dcol, N, Ho, Ho, cout)
             wp = self._packed[f"dec{k}"]
             wD, wS = wp[:cd * 16 * cout], wp[cd * 16 * cout:]
             x_in = rec["inp"][g0 * B * Hi * Hi * cd:g1 * B * Hi * Hi * cd]
             dd = self.buf(f"dec_gd{k}", Md * cd)
-            K.gemm(dcol, wD, dd, Md, cd, 16 * cout)
             if want_wgrad:
                 gw = self.fbuf(f"gwp_dec{k}", 2 * cd * 16 * cout)
-                K.gemm(x_in, dcol, gw[:cd * 16 * cout], cd, 16 * cout, Md, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
-            if want_skip:
-                dcolS = self.buf("scratch_dcolS", Ms * 16 * cout)
-                K.group_sum(dcol, dcolS, self.ix["skip_src"][g0:g1], Gn, nskip, B * Hi * Hi * 16 * cout)
-                dsk = self.buf(f"dskip{k}", Ms * cd)
-                K.gemm(dcolS, wS, dsk, Ms, cd, 16 * cout)
-                rec["dskip"] = dsk
+            if rec["imp"]:
+                # data gradient = stride-2 conv of dy; weight gradients gather dy by filter tap; the skip half works
+                # on dy summed over the calls that share a skip frame (conv is linear) -- no col buffers at all
+                K.conv_gemm(0, dy, wD, dd, N, Hi, Hi, cout, cd)
                 if want_wgrad:
-                    K.gemm(rec["skip"], dcolS, gw[cd * 16 * cout:], cd, 16 * cout, Ms, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
+                    K.conv_gemm(1, x_in, dy, gw[:cd * 16 * cout], N, Hi, Hi, 0, cout, Cm=cd)
+                if want_skip:
+                    dyS = self.buf("scratch_dyS", nskip * B * Ho * Ho * cout)
+                    K.group_sum(dy, dyS, self.ix["skip_src"][g0:g1], Gn, nskip, B * Ho * Ho * cout)
+                    dsk = self.buf(f"dskip{k}", Ms * cd)
+                    K.conv_gemm(0, dyS, wS, dsk, nskip * B, Hi, Hi, cout, cd)
+                    rec["dskip"] = dsk
+                    if want_wgrad:
+                        K.conv_gemm(1, rec["skip"], dyS, gw[cd * 16 * cout:], nskip * B, Hi, Hi, 0, cout, Cm=cd)
+            else:
+                dcol = self.buf("scratch_dcol", Md * 16 * cout)
+                K.im2col(dy, dcol, N, Ho, Ho, cout)
+                K.gemm(dcol, wD, dd, Md, cd, 16 * cout)
+                if want_wgrad:
+                    K.gemm(x_in, dcol, gw[:cd * 16 * cout], cd, 16 * cout, Md, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
+                if want_skip:
+                    dcolS = self.buf("scratch_dcolS", Ms * 16 * cout)
+                    K.group_sum(dcol, dcolS, self.ix["skip_src"][g0:g1], Gn, nskip, B * Hi * Hi * 16 * cout)
+                    dsk = self.buf(f"dskip{k}", Ms * cd)
+                    K.gemm(dcolS, wS, dsk, Ms, cd, 16 * cout)
+                    rec["dskip"] = dsk
+                    if want_wgrad:
+                        K.gemm(rec["skip"], dcolS, gw[cd * 16 * cout:], cd, 16 * cout, Ms, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
             if want_wgrad:
                 K.permute4(gw, A.g[cn + ".weight"], (2 * cd, cout, 4, 4), (16 * cout, 1, 4 * cout, cout))
             dy = dd
@@ -759,13 +791,19 @@ class TrainEngine:
             K.bn_param_grad(st["sdz"], st["sdzx"], T, cout, A.g[bn + ".weight"], A.g[bn + ".bias"])
             K.colsum(gy, M, cout, cout, A.g[cn + ".bias"])
             gw = self.fbuf(f"gwp_enc{l}", cout * 16 * cin)
-            K.gemm(gy, rec["col"], gw, cout, 16 * cin, M, a_mn=True, b_mn=True, lda=cout, ldb=16 * cin)
+            if rec["imp"]:
+                K.conv_gemm(1, gy, rec["inp"], gw, N, Ho, Ho, 0, cin, Cm=cout)
+            else:
+                K.gemm(gy, rec["col"], gw, cout, 16 * cin, M, a_mn=True, b_mn=True, lda=cout, ldb=16 * cin)
             K.permute4(gw, A.g[cn + ".weight"], (cout, cin, 4, 4), (16 * cin, 1, 4 * cin, cin))
             if l > 0:
-                dcol = self.buf("scratch_dcol", M * 16 * cin)
-                K.gemm(gy, self._packed[f"enc{l}"], dcol, M, 16 * cin, cout, b_mn=True)
                 gprev = self.buf(f"enc_gy{l - 1}", N * rec["Hin"] * rec["Hin"] * cin)
-                K.col2im(dcol, gprev, N, Ho, Ho, cin)
+                if rec["imp"]:
+                    K.conv_gemm(2, gy, self._packed[f"enc{l}"], gprev, N, Ho, Ho, cout, cin)
+                else:
+                    dcol = self.buf("scratch_dcol", M * 16 * cin)
+                    K.gemm(gy, self._packed[f"enc{l}"], dcol, M, 16 * cin, cout, b_mn=True)
+                    K.col2im(dcol, gprev, N, Ho, Ho, cin)
                 gy = gprev
 
     def backward_prior(self, plan):
