@@ -149,6 +149,7 @@ class TrainEngine:
         import os
         self.implicit = (act_dtype == torch.bfloat16) and hasattr(kernels, "conv_gemm") and os.environ.get("P2PVG_IMPLICIT", "1") != "0"
         self.last_plan = None
+        self.phase_events = None
 
     # ------------------------------------------------------------------ memory
     def buf(self, name, numel, dtype=None):
@@ -309,26 +310,45 @@ class TrainEngine:
         self.K.launches += st[1]
         return self._bufs["loss_out"][:4]
 
+    def _mark(self, name):
+        """Phase timing for profiling (eager mode only): tools/profile_step.py --phases."""
+        if self.phase_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.phase_events.append((name, e))
+
     def _run(self, x, plan):
+        self._run_inner(x, plan)
+        self._mark("end")
+        return self._bufs["loss_out"][:4]
+
+    def _run_inner(self, x, plan):
+        self._mark("start")
         if hasattr(self.K, "set_fp32_gemm_mode"):
             self.K.set_fp32_gemm_mode(1 if self.tc_lstm else 0)
         self.pack_weights()
         self.pack_lstm_weights()
+        self._mark("pack")
         self.encode(x, plan)
+        self._mark("encode_fwd")
         self.recurrent_fwd(plan)
+        self._mark("lstm_fwd")
         self.decode(plan)
         self.losses_fwd(plan)
+        self._mark("decode_fwd")
         self.backward_main(plan)
+        self._mark("encoder_bwd")
         if self.mode == "A":
             self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
             self.pack_weights(("decoder",))
             self.pack_lstm_weights()
+            self._mark("adam4+repack")
             self.backward_prior(plan)
         else:
             self.backward_prior(plan)
             self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
+        self._mark("prior_bwd")
         self.adam(("prior",))
-        return self._bufs["loss_out"][:4]
 
     # -- Phase E ----------------------------------------------------------------------------
     def encode(self, x, plan):
@@ -713,6 +733,7 @@ class TrainEngine:
         self.d_hpred[:(S + 1) * B * g].zero_()
         self.dH[:T * B * g].zero_()
         self.decoder_backward(0, S, want_wgrad=True, want_skip=True)
+        self._mark("decoder_bwd")
         # alignment loss (value + gradients into d_hpred / dH)
         K.align(self.Hlat, self.ix["in_idx"], self.h_pred, S - 1, B, g, float(opt["weight_align"]), self.align_partial,
                 self.d_hpred, self.dH)
@@ -752,6 +773,7 @@ class TrainEngine:
         K.gather_add_cols(self.dH, dXprior, ix["in_idx"], S, T, B, g, win, 0)
         K.gather_add_cols(self.dH, dXprior, ix["glob_idx"], S, T, B, g, win, g)
         K.gather_add_cols(self.dH, dXpred, ix["in_idx"], S, T, B, g, wp, 0)
+        self._mark("lstm_bwd")
         self.encoder_backward(plan)
 
     def encoder_backward(self, plan):

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--seq", type=int, default=30)
+ap.add_argument("--phases", action="store_true")
 args = ap.parse_args()
 os.environ["P2PVG_GRAPH"] = "0"
 opt = types.SimpleNamespace(dataset="mnist", backbone_net=dcgan_64, lr=1e-3, beta1=0.9, beta=1e-4, weight_cpc=100.0, weight_align=0.5,
@@ -29,6 +30,12 @@ x = torch.rand(args.seq, args.batch, 1, 64, 64, device="cuda")
 eng = model.engine(64)
 for i in range(args.steps):
     n0 = eng.K.launches
+    eng.phase_events = [] if args.phases else None
     out = eng.step(x, use_graph=False, return_device=True)
     torch.cuda.synchronize()
+    if args.phases and i == args.steps - 1:
+        ev = eng.phase_events
+        for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
+            print(f"  phase {name:14s} {a.elapsed_time(b):8.3f} ms")
+        print(f"  total {ev[0][1].elapsed_time(ev[-1][1]):8.3f} ms")
     print(f"step {i}: {eng.K.launches - n0} kernel launches, losses {out.tolist()}", flush=True)
