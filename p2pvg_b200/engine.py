@@ -147,6 +147,8 @@ class TrainEngine:
         # bf16 mode: 4x4/s2 (transposed) convolutions with >= 64 channels on both sides run as implicit GEMMs (4-D TMA
         # pixel-box gathers), without im2col / col2im buffers; P2PVG_IMPLICIT=0 keeps the explicit lowering
         import os
+        # one persistent cooperative launch per LSTM layer and direction instead of two launches per timestep
+        self.fused_scan = hasattr(kernels, "lstm_scan_fwd") and self.R % 64 == 0 and os.environ.get("P2PVG_FUSED_SCAN", "1") != "0"
         self.implicit = (act_dtype == torch.bfloat16) and hasattr(kernels, "conv_gemm") and os.environ.get("P2PVG_IMPLICIT", "1") != "0"
         self.last_plan = None
         self.phase_events = None
@@ -451,7 +453,11 @@ class TrainEngine:
             cs[:B * R].zero_()
             K.gemm(inp, P[f"lstm.{l}.weight_ih"], Pre, rows, 4 * R, R, bias=P[f"lstm.{l}.bias_ih"])
             whh, bhh = P[f"lstm.{l}.weight_hh"], P[f"lstm.{l}.bias_hh"]
-            for s in range(steps):
+            if self.fused_scan:
+                ctr = self.buf("scan_counter", 4, torch.int32)
+                ctr.zero_()
+                K.lstm_scan_fwd(Pre, whh, bhh, gates, hs, cs, steps, B, R, ctr)
+            for s in range(0 if not self.fused_scan else steps, steps):
                 gs = gates[s * B * 4 * R:(s + 1) * B * 4 * R]
                 K.gemm(hs[s * B * R:(s + 1) * B * R], whh, gs, B, 4 * R, R, bias=bhh, addend=Pre[s * B * 4 * R:(s + 1) * B * 4 * R])
                 K.lstm_pointwise_fwd(gs, cs[s * B * R:(s + 1) * B * R], cs[(s + 1) * B * R:(s + 2) * B * R],
@@ -681,7 +687,11 @@ class TrainEngine:
             dht = self.fbuf(f"{m}_dht", B * R)
             whh = P[f"lstm.{l}.weight_hh"]
             dc_next = None
-            for s in range(steps - 1, -1, -1):
+            if self.fused_scan:
+                ctr = self.buf("scan_counter", 4, torch.int32)
+                ctr.zero_()
+                K.lstm_scan_bwd(dH, whh, lay["gates"], lay["cs"], dG, steps, B, R, ctr)
+            for s in (range(steps - 1, -1, -1) if not self.fused_scan else ()):
                 dh_s = dH[s * B * R:(s + 1) * B * R]
                 if s < steps - 1:
                     # dh_total = dH[s] + dG[s+1] . W_hh

@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--seq", type=int, default=30)
 ap.add_argument("--phases", action="store_true")
+ap.add_argument("--calls", action="store_true", help="time every kernel-API call with CUDA events (last step)")
 args = ap.parse_args()
 os.environ["P2PVG_GRAPH"] = "0"
 opt = types.SimpleNamespace(dataset="mnist", backbone_net=dcgan_64, lr=1e-3, beta1=0.9, beta=1e-4, weight_cpc=100.0, weight_align=0.5,
@@ -28,7 +29,32 @@ torch.manual_seed(1)
 model = P2PModel(args.batch, 1, 128, 10, 256, 1, 1, 2, opt=opt).cuda()
 x = torch.rand(args.seq, args.batch, 1, 64, 64, device="cuda")
 eng = model.engine(64)
+calls = []
+
+
+def wrap_kernels(K):
+    import inspect
+    for name, fn in inspect.getmembers(K, predicate=inspect.ismethod):
+        if name.startswith("_") or name in ("gemm_workspace", "bn_workspace", "set_gemm_impl", "set_fp32_gemm_mode", "has_tcgen05", "mse_chunks"):
+            continue
+
+        def make(name, fn):
+            def w(*a, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **kw)
+                e1.record()
+                ints = [str(v) for v in a if isinstance(v, int)][:7]
+                calls.append((name, ",".join(ints), e0, e1, len(eng.phase_events) if eng.phase_events is not None else 0))
+                return r
+            return w
+        setattr(K, name, make(name, fn))
+
+
 for i in range(args.steps):
+    if args.calls and i == args.steps - 1:
+        wrap_kernels(eng.K)
+        args.phases = True
     n0 = eng.K.launches
     eng.phase_events = [] if args.phases else None
     out = eng.step(x, use_graph=False, return_device=True)
@@ -38,4 +64,18 @@ for i in range(args.steps):
         for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
             print(f"  phase {name:14s} {a.elapsed_time(b):8.3f} ms")
         print(f"  total {ev[0][1].elapsed_time(ev[-1][1]):8.3f} ms")
+    if args.calls and i == args.steps - 1:
+        names = [n for n, _ in eng.phase_events]
+        rows = [(c[2].elapsed_time(c[3]), c[0], c[1], names[min(c[4], len(names) - 1)]) for c in calls]
+        from collections import defaultdict
+        agg = defaultdict(lambda: [0, 0.0])
+        for ms, nm, dims, ph in rows:
+            agg[(ph, nm)][0] += 1
+            agg[(ph, nm)][1] += ms
+        print("  per phase / op (CUDA-event time incl. launch gaps):")
+        for (ph, nm), (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+            print(f"    {ph:13s} {nm:20s} n={cnt:4d} {ms:8.3f} ms")
+        print("  slowest single calls:")
+        for ms, nm, dims, ph in sorted(rows, reverse=True)[:40]:
+            print(f"    {ms:7.3f} ms {ph:13s} {nm:14s} {dims}")
     print(f"step {i}: {eng.K.launches - n0} kernel launches, losses {out.tolist()}", flush=True)
