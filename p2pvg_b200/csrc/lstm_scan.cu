@@ -204,7 +204,7 @@ lstm_scan_bwd_kernel(const float* __restrict__ dhtop, const float* __restrict__ 
   }
 }
 
-int g_fwd_attr = 0, g_bwd_attr = 0;
+size_t g_fwd_attr = 0, g_bwd_attr = 0;  // largest dynamic shared memory size enabled so far
 
 }  // namespace
 
@@ -214,10 +214,10 @@ int p2pvg_lstm_scan_fwd_impl(const float* pre, const float* whh, const float* bh
   P2PVG_REQUIRE(R % 8 == 0 && R % 4 == 0, P2PVG_ERR_UNSUPPORTED, "lstm_scan: hidden size %d must be a multiple of 8", R);
   const size_t smem = (size_t)(32 * (R + PAD) + RB * (R + PAD) + RB * 33) * sizeof(float);
   P2PVG_REQUIRE(smem <= 227 * 1024, P2PVG_ERR_UNSUPPORTED, "lstm_scan_fwd: hidden size %d needs %zu B of shared memory", R, smem);
-  if (!g_fwd_attr) {
+  if (smem > g_fwd_attr) {
     cudaError_t e = cudaFuncSetAttribute(lstm_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { p2pvg_set_error("lstm_scan_fwd: %s", cudaGetErrorString(e)); return P2PVG_ERR_CUDA; }
-    g_fwd_attr = 1;
+    g_fwd_attr = smem;
   }
   const int grid = (R / UB) * cdiv(B, RB);
   void* args[] = {(void*)&pre, (void*)&whh, (void*)&bhh, (void*)&gates, (void*)&hs, (void*)&cs, (void*)&S, (void*)&B, (void*)&R, (void*)&counter};
@@ -236,10 +236,10 @@ int p2pvg_lstm_scan_bwd_impl(const float* dhtop, const float* whh, const float* 
   P2PVG_REQUIRE(R % 64 == 0, P2PVG_ERR_UNSUPPORTED, "lstm_scan_bwd: hidden size %d must be a multiple of 64", R);
   const size_t smem = (size_t)(UB * (4 * R + PAD) + RB * (256 + PAD)) * sizeof(float);
   P2PVG_REQUIRE(smem <= 227 * 1024, P2PVG_ERR_UNSUPPORTED, "lstm_scan_bwd: hidden size %d needs %zu B of shared memory", R, smem);
-  if (!g_bwd_attr) {
+  if (smem > g_bwd_attr) {
     cudaError_t e = cudaFuncSetAttribute(lstm_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { p2pvg_set_error("lstm_scan_bwd: %s", cudaGetErrorString(e)); return P2PVG_ERR_CUDA; }
-    g_bwd_attr = 1;
+    g_bwd_attr = smem;
   }
   const int grid = (R / UB) * cdiv(B, RB);
   void* args[] = {(void*)&dhtop, (void*)&whh, (void*)&gates, (void*)&cs, (void*)&dG, (void*)&S, (void*)&B, (void*)&R, (void*)&counter};
