@@ -112,11 +112,12 @@ int p2pvg_lstm_pointwise_bwd(const float* dh, const float* dc_next, const float*
  *   forward : gates_s = pre_s + b_hh + h_{s-1}.W_hh^T -> (i,f,g,o) -> c_s, h_s       pre [S,B,4R] = x-part incl. b_ih
  *             gates [S,B,4R] out (activations), hs / cs [S+1,B,R] with slot 0 = initial state (zeros, models/lstm.py:21-27)
  *   backward: dh_s = dhtop_s + dG_{s+1}.W_hh, cell backward -> dG [S,B,4R] (gradient w.r.t. the gate pre-activations)
- * `counter` is a zero-initialised uint32 in device memory (the grid barrier); R %% 64 == 0. */
+ * `counter` is a zero-initialised uint32 in device memory (the grid barrier); R %% 64 == 0, R <= 256.
+ * tf32 = 0: exact fp32 FFMA products (parity mode); tf32 = 1: the recurrent products on the tensor cores (mma.sync tf32). */
 int p2pvg_lstm_scan_fwd(const float* pre, const float* whh, const float* bhh, float* gates, float* hs, float* cs, int S, int B, int R,
-                        unsigned* counter, void* stream);
+                        int tf32, unsigned* counter, void* stream);
 int p2pvg_lstm_scan_bwd(const float* dhtop, const float* whh, const float* gates, const float* cs, float* dG, int S, int B, int R,
-                        unsigned* counter, void* stream);
+                        int tf32, unsigned* counter, void* stream);
 /* gaussian_lstm.reparameterize (models/lstm.py:76-81) for posterior and prior + KLCriterion.forward
  * (misc/criterion.py:10-15) summed over all elements (division by opt.batch_size happens in finalize_losses). */
 int p2pvg_reparam_kl_fwd(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,

@@ -184,13 +184,13 @@ class CudaKernels:
         self._ck(self.lib.p2pvg_lstm_pointwise_bwd(_p(dh), _p(dc_next), _p(gates), _p(c_prev), _p(c), _p(dgates), _p(dc_prev), _i(B),
                                                    _i(R), self._stream()))
 
-    def lstm_scan_fwd(self, pre, whh, bhh, gates, hs, cs, S, B, R, counter):
-        self._ck(self.lib.p2pvg_lstm_scan_fwd(_p(pre), _p(whh), _p(bhh), _p(gates), _p(hs), _p(cs), _i(S), _i(B), _i(R), _p(counter),
-                                              self._stream()))
+    def lstm_scan_fwd(self, pre, whh, bhh, gates, hs, cs, S, B, R, counter, tf32=False):
+        self._ck(self.lib.p2pvg_lstm_scan_fwd(_p(pre), _p(whh), _p(bhh), _p(gates), _p(hs), _p(cs), _i(S), _i(B), _i(R), _i(int(tf32)),
+                                              _p(counter), self._stream()))
 
-    def lstm_scan_bwd(self, dhtop, whh, gates, cs, dG, S, B, R, counter):
-        self._ck(self.lib.p2pvg_lstm_scan_bwd(_p(dhtop), _p(whh), _p(gates), _p(cs), _p(dG), _i(S), _i(B), _i(R), _p(counter),
-                                              self._stream()))
+    def lstm_scan_bwd(self, dhtop, whh, gates, cs, dG, S, B, R, counter, tf32=False):
+        self._ck(self.lib.p2pvg_lstm_scan_bwd(_p(dhtop), _p(whh), _p(gates), _p(cs), _p(dG), _i(S), _i(B), _i(R), _i(int(tf32)),
+                                              _p(counter), self._stream()))
 
     def reparam_kl_fwd(self, mu, lv, mu_p, lv_p, eps, eps_p, z, z_p, n, kl_sum):
         self._ck(self.lib.p2pvg_reparam_kl_fwd(_p(mu), _p(lv), _p(mu_p), _p(lv_p), _p(eps), _p(eps_p), _p(z), _p(z_p), _i(n),

@@ -33,7 +33,21 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   __syncthreads();
 }
 
+// legacy warp-level tensor-core MMA (TF32 operands, fp32 accumulate): D[16x8] += A[16x8] . B[8x8]
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
+// TC = false: exact fp32 FFMA recurrence (parity mode).  TC = true: the h.W_hh^T product on the tensor cores (TF32).
+template <bool TC>
 __global__ void __launch_bounds__(NT, 1)
 lstm_scan_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ whh, const float* __restrict__ bhh,
                      float* __restrict__ gates, float* __restrict__ hs, float* __restrict__ cs, int S, int B, int R,
@@ -82,6 +96,31 @@ lstm_scan_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
       *reinterpret_cast<float4*>(Hs + row * LD + k4 * 4) = v;
     }
     __syncthreads();
+    if (TC) {
+      // 64x32 output = 4 (m16) x 4 (n8) MMA tiles; warp w: m-tile w>>1, n-tiles 2*(w&1)+{0,1}
+      const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+      const int m0 = (warp >> 1) * 16, nb = (warp & 1) * 16;
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* ha = Hs + (m0 + gq) * LD + tq;
+      const float* wb0 = Ws + (nb + gq) * LD + tq;
+      const float* wb1 = wb0 + 8 * LD;
+      for (int k = 0; k < R; k += 8) {
+        uint32_t a[4], b0[2], b1[2];
+        a[0] = to_tf32(ha[k]); a[1] = to_tf32(ha[8 * LD + k]); a[2] = to_tf32(ha[k + 4]); a[3] = to_tf32(ha[8 * LD + k + 4]);
+        b0[0] = to_tf32(wb0[k]); b0[1] = to_tf32(wb0[k + 4]);
+        b1[0] = to_tf32(wb1[k]); b1[1] = to_tf32(wb1[k + 4]);
+        mma_tf32(c0, a, b0);
+        mma_tf32(c1, a, b1);
+      }
+      Gs[(m0 + gq) * 33 + nb + 2 * tq] = c0[0];
+      Gs[(m0 + gq) * 33 + nb + 2 * tq + 1] = c0[1];
+      Gs[(m0 + gq + 8) * 33 + nb + 2 * tq] = c0[2];
+      Gs[(m0 + gq + 8) * 33 + nb + 2 * tq + 1] = c0[3];
+      Gs[(m0 + gq) * 33 + nb + 8 + 2 * tq] = c1[0];
+      Gs[(m0 + gq) * 33 + nb + 8 + 2 * tq + 1] = c1[1];
+      Gs[(m0 + gq + 8) * 33 + nb + 8 + 2 * tq] = c1[2];
+      Gs[(m0 + gq + 8) * 33 + nb + 8 + 2 * tq + 1] = c1[3];
+    } else {
     float acc[4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
@@ -105,6 +144,7 @@ lstm_scan_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
     for (int i = 0; i < 4; i++) {
       Gs[(tr + i) * 33 + tc] = acc[i][0];
       Gs[(tr + i) * 33 + tc + 1] = acc[i][1];
+    }
     }
     __syncthreads();
     // pointwise LSTM cell for (row, unit) = (pr0 + 32h, puu)
@@ -131,6 +171,7 @@ lstm_scan_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+template <bool TC>
 __global__ void __launch_bounds__(NT, 1)
 lstm_scan_bwd_kernel(const float* __restrict__ dhtop, const float* __restrict__ whh, const float* __restrict__ gates,
                      const float* __restrict__ cs, float* __restrict__ dG, int S, int B, int R, unsigned* __restrict__ counter) {
@@ -140,6 +181,7 @@ lstm_scan_bwd_kernel(const float* __restrict__ dhtop, const float* __restrict__ 
   const int LDW = K4 + PAD, LDG = KC + PAD;
   float* Wt = sm;                     // [UB][LDW]   Wt[uu][q] = W_hh[q][u0+uu]
   float* Gc = Wt + UB * LDW;          // [RB][LDG]   chunk of dG_{s+1}
+  float* Rs = Gc + RB * LDG;          // [2][RB][9]  TC: partial dh_rec of the two K halves
   const int nub = R / UB;
   const int ub = blockIdx.x % nub, rb = blockIdx.x / nub;
   const int u0 = ub * UB, r0 = rb * RB;
@@ -160,6 +202,10 @@ lstm_scan_bwd_kernel(const float* __restrict__ dhtop, const float* __restrict__ 
     if (it > 0) {
       grid_barrier(counter, nctas * (unsigned)it);   // dG_{s+1} complete everywhere
       const float* gnext = dG + (long long)(s + 1) * B * K4;
+      // TC: warp w -> m-tile (w&3), K half (w>>2); accumulates over all chunks in registers
+      const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+      const int m0 = (warp & 3) * 16, kh = (warp >> 2) * 128;
+      float cacc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int kc = 0; kc < K4; kc += KC) {
         for (int i = tid; i < RB * (KC / 4); i += NT) {
           const int row = i / (KC / 4), k4 = i - row * (KC / 4);
@@ -168,6 +214,17 @@ lstm_scan_bwd_kernel(const float* __restrict__ dhtop, const float* __restrict__ 
           *reinterpret_cast<float4*>(Gc + row * LDG + k4 * 4) = v;
         }
         __syncthreads();
+        if (TC) {
+          const float* ga = Gc + (m0 + gq) * LDG + kh + tq;
+          const float* wb = Wt + gq * LDW + kc + kh + tq;
+#pragma unroll 4
+          for (int k = 0; k < 128; k += 8) {
+            uint32_t a[4], b[2];
+            a[0] = to_tf32(ga[k]); a[1] = to_tf32(ga[8 * LDG + k]); a[2] = to_tf32(ga[k + 4]); a[3] = to_tf32(ga[8 * LDG + k + 4]);
+            b[0] = to_tf32(wb[k]); b[1] = to_tf32(wb[k + 4]);
+            mma_tf32(cacc, a, b);
+          }
+        } else {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const float* grow = Gc + (pr0 + 32 * h) * LDG;
@@ -181,7 +238,18 @@ lstm_scan_bwd_kernel(const float* __restrict__ dhtop, const float* __restrict__ 
           }
           rec[h] += a0 + a1;
         }
+        }
         __syncthreads();
+      }
+      if (TC) {
+        float* dst = Rs + (warp >> 2) * RB * 9;
+        dst[(m0 + gq) * 9 + 2 * tq] = cacc[0];
+        dst[(m0 + gq) * 9 + 2 * tq + 1] = cacc[1];
+        dst[(m0 + gq + 8) * 9 + 2 * tq] = cacc[2];
+        dst[(m0 + gq + 8) * 9 + 2 * tq + 1] = cacc[3];
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; h++) rec[h] = Rs[(pr0 + 32 * h) * 9 + puu] + Rs[RB * 9 + (pr0 + 32 * h) * 9 + puu];
       }
     }
 #pragma unroll
@@ -209,19 +277,21 @@ size_t g_fwd_attr = 0, g_bwd_attr = 0;  // largest dynamic shared memory size en
 }  // namespace
 
 int p2pvg_lstm_scan_fwd_impl(const float* pre, const float* whh, const float* bhh, float* gates, float* hs, float* cs, int S, int B,
-                             int R, unsigned* counter, cudaStream_t st) {
+                             int R, int tf32, unsigned* counter, cudaStream_t st) {
   if (S <= 0 || B <= 0) return P2PVG_OK;
   P2PVG_REQUIRE(R % 8 == 0 && R % 4 == 0, P2PVG_ERR_UNSUPPORTED, "lstm_scan: hidden size %d must be a multiple of 8", R);
   const size_t smem = (size_t)(32 * (R + PAD) + RB * (R + PAD) + RB * 33) * sizeof(float);
   P2PVG_REQUIRE(smem <= 227 * 1024, P2PVG_ERR_UNSUPPORTED, "lstm_scan_fwd: hidden size %d needs %zu B of shared memory", R, smem);
   if (smem > g_fwd_attr) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lstm_scan_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_scan_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { p2pvg_set_error("lstm_scan_fwd: %s", cudaGetErrorString(e)); return P2PVG_ERR_CUDA; }
     g_fwd_attr = smem;
   }
   const int grid = (R / UB) * cdiv(B, RB);
   void* args[] = {(void*)&pre, (void*)&whh, (void*)&bhh, (void*)&gates, (void*)&hs, (void*)&cs, (void*)&S, (void*)&B, (void*)&R, (void*)&counter};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_scan_fwd_kernel, dim3(grid), dim3(NT), args, smem, st);
+  const void* kfn = tf32 ? (const void*)lstm_scan_fwd_kernel<true> : (const void*)lstm_scan_fwd_kernel<false>;
+  cudaError_t e = cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(NT), args, smem, st);
   if (e != cudaSuccess) {
     p2pvg_set_error("lstm_scan_fwd: cooperative launch of %d CTAs failed: %s", grid, cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -231,19 +301,21 @@ int p2pvg_lstm_scan_fwd_impl(const float* pre, const float* whh, const float* bh
 }
 
 int p2pvg_lstm_scan_bwd_impl(const float* dhtop, const float* whh, const float* gates, const float* cs, float* dG, int S, int B, int R,
-                             unsigned* counter, cudaStream_t st) {
+                             int tf32, unsigned* counter, cudaStream_t st) {
   if (S <= 0 || B <= 0) return P2PVG_OK;
   P2PVG_REQUIRE(R % 64 == 0, P2PVG_ERR_UNSUPPORTED, "lstm_scan_bwd: hidden size %d must be a multiple of 64", R);
-  const size_t smem = (size_t)(UB * (4 * R + PAD) + RB * (256 + PAD)) * sizeof(float);
+  const size_t smem = (size_t)(UB * (4 * R + PAD) + RB * (256 + PAD) + 2 * RB * 9) * sizeof(float);
   P2PVG_REQUIRE(smem <= 227 * 1024, P2PVG_ERR_UNSUPPORTED, "lstm_scan_bwd: hidden size %d needs %zu B of shared memory", R, smem);
   if (smem > g_bwd_attr) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lstm_scan_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_scan_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { p2pvg_set_error("lstm_scan_bwd: %s", cudaGetErrorString(e)); return P2PVG_ERR_CUDA; }
     g_bwd_attr = smem;
   }
   const int grid = (R / UB) * cdiv(B, RB);
   void* args[] = {(void*)&dhtop, (void*)&whh, (void*)&gates, (void*)&cs, (void*)&dG, (void*)&S, (void*)&B, (void*)&R, (void*)&counter};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_scan_bwd_kernel, dim3(grid), dim3(NT), args, smem, st);
+  const void* kfn = tf32 ? (const void*)lstm_scan_bwd_kernel<true> : (const void*)lstm_scan_bwd_kernel<false>;
+  cudaError_t e = cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(NT), args, smem, st);
   if (e != cudaSuccess) {
     p2pvg_set_error("lstm_scan_bwd: cooperative launch of %d CTAs failed: %s", grid, cudaGetErrorString(e));
     (void)cudaGetLastError();

@@ -148,7 +148,7 @@ class TrainEngine:
         # pixel-box gathers), without im2col / col2im buffers; P2PVG_IMPLICIT=0 keeps the explicit lowering
         import os
         # one persistent cooperative launch per LSTM layer and direction instead of two launches per timestep
-        self.fused_scan = hasattr(kernels, "lstm_scan_fwd") and self.R % 64 == 0 and os.environ.get("P2PVG_FUSED_SCAN", "1") != "0"
+        self.fused_scan = hasattr(kernels, "lstm_scan_fwd") and self.R % 64 == 0 and self.R <= 256 and os.environ.get("P2PVG_FUSED_SCAN", "1") != "0"
         self.implicit = (act_dtype == torch.bfloat16) and hasattr(kernels, "conv_gemm") and os.environ.get("P2PVG_IMPLICIT", "1") != "0"
         self.last_plan = None
         self.phase_events = None
@@ -456,7 +456,7 @@ class TrainEngine:
             if self.fused_scan:
                 ctr = self.buf("scan_counter", 4, torch.int32)
                 ctr.zero_()
-                K.lstm_scan_fwd(Pre, whh, bhh, gates, hs, cs, steps, B, R, ctr)
+                K.lstm_scan_fwd(Pre, whh, bhh, gates, hs, cs, steps, B, R, ctr, tf32=self.tc_lstm)
             for s in range(0 if not self.fused_scan else steps, steps):
                 gs = gates[s * B * 4 * R:(s + 1) * B * 4 * R]
                 K.gemm(hs[s * B * R:(s + 1) * B * R], whh, gs, B, 4 * R, R, bias=bhh, addend=Pre[s * B * 4 * R:(s + 1) * B * 4 * R])
@@ -690,7 +690,7 @@ class TrainEngine:
             if self.fused_scan:
                 ctr = self.buf("scan_counter", 4, torch.int32)
                 ctr.zero_()
-                K.lstm_scan_bwd(dH, whh, lay["gates"], lay["cs"], dG, steps, B, R, ctr)
+                K.lstm_scan_bwd(dH, whh, lay["gates"], lay["cs"], dG, steps, B, R, ctr, tf32=self.tc_lstm)
             for s in (range(steps - 1, -1, -1) if not self.fused_scan else ()):
                 dh_s = dH[s * B * R:(s + 1) * B * R]
                 if s < steps - 1:
