@@ -93,9 +93,10 @@ int p2pvg_bn_fwd_stats(const void* x, int dtype, int G, int64_t R, int C, const 
                        void* stream);
 int p2pvg_bn_act(const void* x, void* y, int dtype, const float* scale, const float* shift, int G, int64_t R, int C, int act,
                  void* stream);
+/* y may be NULL for LeakyReLU: the activation derivative is then recomputed from sign(x*scale+shift) (saves one read of y). */
 int p2pvg_bn_bwd(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
                  const float* gamma, int G, int64_t R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
-                 float* sum_dzx, void* stream);
+                 float* sum_dzx, const float* scale, const float* shift, void* stream);
 /* eval-mode BatchNorm (running statistics; generate.py / p2p_generate): scale = gamma/sqrt(rvar+eps), shift = beta-rmean*scale */
 int p2pvg_bn_eval_coeffs(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, int C,
                          float* scale, float* shift, void* stream);

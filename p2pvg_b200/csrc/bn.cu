@@ -19,7 +19,9 @@ __device__ __forceinline__ float act_grad(float y, int act) {
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd, int act,
-                                                        long long R, int C, int rows_per_chunk, double2* __restrict__ partial) {
+                                                        long long R, int C, int rows_per_chunk, double2* __restrict__ partial,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift) {
+  // y == nullptr (LeakyReLU only): the activation derivative is recomputed from sign(x*scale+shift) instead of reading y
   constexpr int V = VecN<T>::N;
   const int CV = C / V;
   const int lanes = 256 / CV;
@@ -28,13 +30,18 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
   const long long r0 = (long long)chunk * rows_per_chunk;
   long long r1 = r0 + rows_per_chunk;
   if (r1 > R) r1 = R;
-  float s0[V], s1[V], mu[V], is[V];
+  float s0[V], s1[V], mu[V], is[V], sc[V], sh[V];
+  const bool no_y = (MODE == 1) && (y == nullptr);
 #pragma unroll
   for (int j = 0; j < V; j++) {
-    s0[j] = 0.f; s1[j] = 0.f; mu[j] = 0.f; is[j] = 0.f;
+    s0[j] = 0.f; s1[j] = 0.f; mu[j] = 0.f; is[j] = 0.f; sc[j] = 0.f; sh[j] = 0.f;
     if (MODE == 1) {
       mu[j] = mean[(long long)g * C + cv * V + j];
       is[j] = invstd[(long long)g * C + cv * V + j];
+      if (no_y) {
+        sc[j] = scale[(long long)g * C + cv * V + j];
+        sh[j] = shift[(long long)g * C + cv * V + j];
+      }
     }
   }
   for (long long r = r0 + lane; r < r1; r += 2 * lanes) {
@@ -46,9 +53,12 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
     uint4 da, db, ya, yb;
     if (MODE == 1) {
       da = ld_raw16(dy + off0);
-      ya = ld_raw16(y + off0);
       db = two ? ld_raw16(dy + off1) : make_uint4(0u, 0u, 0u, 0u);
-      yb = two ? ld_raw16(y + off1) : make_uint4(0u, 0u, 0u, 0u);
+      ya = yb = make_uint4(0u, 0u, 0u, 0u);
+      if (!no_y) {
+        ya = ld_raw16(y + off0);
+        if (two) yb = ld_raw16(y + off1);
+      }
     }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -65,7 +75,8 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
           s0[j] += xv[j];
           s1[j] = fmaf(xv[j], xv[j], s1[j]);
         } else {
-          float dz = dv[j] * act_grad(yv[j], act);
+          const float ya_ = no_y ? fmaf(xv[j], sc[j], sh[j]) : yv[j];  // only its sign matters for LeakyReLU
+          float dz = dv[j] * act_grad(ya_, act);
           s0[j] += dz;
           s1[j] = fmaf(dz, (xv[j] - mu[j]) * is[j], s1[j]);
         }
@@ -171,12 +182,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ sum_dz,
                                                            const float* __restrict__ sum_dzx, long long R, int C, long long totalv,
-                                                           int act, T* __restrict__ dx) {
+                                                           int act, T* __restrict__ dx, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift) {
   constexpr int V = VecN<T>::N;
   const int CV = C / V;
   const float invR = 1.f / (float)R;
+  const bool no_y = (y == nullptr);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < totalv; idx += (long long)gridDim.x * blockDim.x) {
-    const uint4 rd = ld_raw16(dy + idx * V), rx = ld_raw16(x + idx * V), ry = ld_raw16(y + idx * V);
+    const uint4 rd = ld_raw16(dy + idx * V), rx = ld_raw16(x + idx * V);
+    const uint4 ry = no_y ? make_uint4(0u, 0u, 0u, 0u) : ld_raw16(y + idx * V);
     const int cv = (int)(idx % CV);
     const int g = (int)((idx / CV) / R);
     float dv[V], xv[V], yv[V], o[V];
@@ -188,7 +202,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
       const long long gc = (long long)g * C + cv * V + j;
       const float is = invstd[gc];
       const float xhat = (xv[j] - mean[gc]) * is;
-      const float dz = dv[j] * act_grad(yv[j], act);
+      const float ya_ = no_y ? fmaf(xv[j], scale[gc], shift[gc]) : yv[j];
+      const float dz = dv[j] * act_grad(ya_, act);
       o[j] = gamma[cv * V + j] * is * (dz - sum_dz[gc] * invR - xhat * sum_dzx[gc] * invR);
     }
     st_raw16(dx + idx * V, pack16<T>(o));
@@ -274,7 +289,7 @@ int p2pvg_bn_fwd_stats_impl(const void* x, int dtype, int G, long long R, int C,
   Chunking ch = choose_chunks(R, C, vec);
   dim3 grid(ch.nchunk, G);
   DISPATCH_DTYPE(dtype, T, (bn_reduce_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, 0, R, C,
-                                                                         ch.rows_per_chunk, (double2*)ws)));
+                                                                         ch.rows_per_chunk, (double2*)ws, nullptr, nullptr)));
   bn_fwd_finalize_kernel<<<cdiv((long long)G * C, 256), 256, 0, st>>>((const double2*)ws, ch.nchunk, G, C, R, gamma, beta, eps, mean,
                                                                       invstd, var_unbiased, scale, shift);
   return p2pvg_check_launch("bn_fwd_stats");
@@ -292,7 +307,9 @@ int p2pvg_bn_act_impl(const void* x, void* y, int dtype, const float* scale, con
 
 int p2pvg_bn_bwd_impl(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
                       const float* gamma, int G, long long R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
-                      float* sum_dzx, cudaStream_t st) {
+                      float* sum_dzx, const float* scale, const float* shift, cudaStream_t st) {
+  P2PVG_REQUIRE(y != nullptr || (act == P2PVG_ACT_LRELU && scale && shift), P2PVG_ERR_BAD_ARG,
+                "bn_bwd: y may only be omitted for LeakyReLU with scale/shift supplied");
   const int vec = dtype == P2PVG_BF16 ? 8 : 4;
   if (int e = check_bn_shape(C, vec, "bn_bwd")) return e;
   P2PVG_REQUIRE(ws_bytes >= p2pvg_bn_workspace_bytes_impl(G, C), P2PVG_ERR_WORKSPACE, "bn_bwd: workspace too small");
@@ -300,11 +317,11 @@ int p2pvg_bn_bwd_impl(const void* dy, const void* x, const void* y, int dtype, c
   Chunking ch = choose_chunks(R, C, vec);
   dim3 grid(ch.nchunk, G);
   DISPATCH_DTYPE(dtype, T, (bn_reduce_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, act, R, C,
-                                                                         ch.rows_per_chunk, (double2*)ws)));
+                                                                         ch.rows_per_chunk, (double2*)ws, scale, shift)));
   bn_bwd_finalize_kernel<<<cdiv((long long)G * C, 256), 256, 0, st>>>((const double2*)ws, ch.nchunk, G, C, sum_dz, sum_dzx);
   long long totalv = (long long)G * R * (C / vec);
   DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<grid_for(totalv, 256), 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, mean, invstd,
-                                                                                          gamma, sum_dz, sum_dzx, R, C, totalv, act, (T*)dx)));
+                                                                                          gamma, sum_dz, sum_dzx, R, C, totalv, act, (T*)dx, scale, shift)));
   return p2pvg_check_launch("bn_bwd");
 }
 

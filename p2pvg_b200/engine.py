@@ -603,11 +603,11 @@ class TrainEngine:
                 st = rec["st"]
                 sl = slice(g0 * B * Ho * Ho * cout, g1 * B * Ho * Ho * cout)
                 c0, c1 = g0 * st["C"], g1 * st["C"]
-                K.bn_bwd(dy, rec["raw"][sl], rec["d"][sl], st["mean"][c0:c1], st["invstd"][c0:c1], st["gamma"], Gn,
-                         B * Ho * Ho, cout, ACT_LRELU, dy, st["sdz"][c0:c1], st["sdzx"][c0:c1])
+                self.bn_backward(dy, rec["raw"][sl], rec["d"][sl], st, c0, c1, Gn, B * Ho * Ho, cout, ACT_LRELU)
                 if want_wgrad:
                     K.bn_param_grad(st["sdz"][c0:c1], st["sdzx"][c0:c1], Gn, cout, A.g[bn + ".weight"], A.g[bn + ".bias"])
-            if want_wgrad:
+                    A.g[cn + ".bias"].zero_()  # bias feeding a training-mode BatchNorm: gradient is exactly zero
+            elif want_wgrad:
                 K.colsum(dy, rows_o, cout, cout, A.g[cn + ".bias"])
             wp = self._packed[f"dec{k}"]
             wD, wS = wp[:cd * 16 * cout], wp[cd * 16 * cout:]
@@ -652,12 +652,11 @@ class TrainEngine:
         st = self.dec_first["st"]
         sl = slice(g0 * B * 16 * ctop, g1 * B * 16 * ctop)
         c0, c1 = g0 * ctop, g1 * ctop
-        K.bn_bwd(dy, self.dec_first["raw"][sl], self.dec_first["d"][sl], st["mean"][c0:c1], st["invstd"][c0:c1], st["gamma"], Gn,
-                 B * 16, ctop, ACT_LRELU, dy, st["sdz"][c0:c1], st["sdzx"][c0:c1])
+        self.bn_backward(dy, self.dec_first["raw"][sl], self.dec_first["d"][sl], st, c0, c1, Gn, B * 16, ctop, ACT_LRELU)
         hp = self.dec_first["inp"][g0 * B * g:g1 * B * g]
         if want_wgrad:
             K.bn_param_grad(st["sdz"][c0:c1], st["sdzx"][c0:c1], Gn, ctop, A.g[bn + ".weight"], A.g[bn + ".bias"])
-            K.colsum(dy, N * 16, ctop, ctop, A.g[cn + ".bias"])
+            A.g[cn + ".bias"].zero_()
             gw = self.fbuf("gwp_dec-1", g * 16 * ctop)
             K.gemm(hp, dy, gw, g, 16 * ctop, N, a_mn=True, b_mn=True, lda=g, ldb=16 * ctop)
             K.permute4(gw, A.g[cn + ".weight"], (g, ctop, 4, 4), (16 * ctop, 1, 4 * ctop, ctop))
@@ -668,6 +667,17 @@ class TrainEngine:
             tmp = self.buf("dhp_act", N * g)
             K.gemm(dy, self._packed["dec-1"], tmp, N, g, 16 * ctop)
             K.permute4(tmp, dhp, (N * g, 1, 1, 1), (1, 0, 0, 0))
+
+    def bn_backward(self, dy, raw, y, st, c0, c1, G, R, C, act):
+        """BatchNorm + activation backward in place (dy -> d raw).  On the CUDA backend the LeakyReLU derivative is
+        recomputed from sign(raw*scale+shift), so the activation tensor is not read again."""
+        K = self.K
+        if getattr(K, "name", "") == "cuda" and act == ACT_LRELU:
+            K.bn_bwd(dy, raw, None, st["mean"][c0:c1], st["invstd"][c0:c1], st["gamma"], G, R, C, act, dy, st["sdz"][c0:c1],
+                     st["sdzx"][c0:c1], scale=st["scale"][c0:c1], shift=st["shift"][c0:c1])
+        else:
+            K.bn_bwd(dy, raw, y, st["mean"][c0:c1], st["invstd"][c0:c1], st["gamma"], G, R, C, act, dy, st["sdz"][c0:c1],
+                     st["sdzx"][c0:c1])
 
     def lstm_backward(self, m, dtop, steps, want_wgrad, want_dx, dx_out=None):
         """Reverse-time scan.  dtop: [steps*B, R] gradient w.r.t. the top layer's hidden outputs (it is
@@ -801,7 +811,7 @@ class TrainEngine:
         st = fin["st"]
         K.bn_bwd(dy, fin["raw"], fin["y"], st["mean"], st["invstd"], st["gamma"], T, B, g, ACT_TANH, dy, st["sdz"], st["sdzx"])
         K.bn_param_grad(st["sdz"], st["sdzx"], T, g, A.g[bn + ".weight"], A.g[bn + ".bias"])
-        K.colsum(dy, N, g, g, A.g[cn + ".bias"])
+        A.g[cn + ".bias"].zero_()
         ctop = self.chans[-1]
         gw = self.fbuf(f"gwp_enc{n}", g * 16 * ctop)
         K.gemm(dy, fin["inp"], gw, g, 16 * ctop, N, a_mn=True, b_mn=True, lda=g, ldb=16 * ctop)
@@ -818,10 +828,9 @@ class TrainEngine:
                 K.add_indexed(gy, dsk, self.ix["skip_dst"], nskip, B * Ho * Ho * cout)
             cn, bn = self.enc_names(l)
             st = rec["st"]
-            K.bn_bwd(gy, rec["raw"], rec["y"], st["mean"], st["invstd"], st["gamma"], T, B * Ho * Ho, cout, ACT_LRELU, gy,
-                     st["sdz"], st["sdzx"])
+            self.bn_backward(gy, rec["raw"], rec["y"], st, 0, T * cout, T, B * Ho * Ho, cout, ACT_LRELU)
             K.bn_param_grad(st["sdz"], st["sdzx"], T, cout, A.g[bn + ".weight"], A.g[bn + ".bias"])
-            K.colsum(gy, M, cout, cout, A.g[cn + ".bias"])
+            A.g[cn + ".bias"].zero_()
             gw = self.fbuf(f"gwp_enc{l}", cout * 16 * cin)
             if rec["imp"]:
                 K.conv_gemm(1, gy, rec["inp"], gw, N, Ho, Ho, 0, cin, Cm=cout)
