@@ -71,6 +71,17 @@ int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c
                     int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
                     void* workspace, size_t ws_bytes, void* stream);
 
+/* Thin ends of the dcgan stacks (1 or 3 image channels on one side; HBM-bound direct kernels, fp32 master weights):
+ *   conv_thin_in : y[N,H/2,W/2,Co] = conv4x4/s2/p1(x[N,H,W,Ci<=4]) . w[Co][Ci][4][4] + bias   — encoder c1 forward
+ *                  (models/dcgan_64.py:34) and the data-gradient of the last decoder layer (its ConvT weight [Cin][nc][4][4]
+ *                  has this layout with Co = Cin)
+ *   convT_thin_out: y[N,2H,2W,Co<=3] = convT4x4/s2/p1(x[N,H,W,Ci]) . w[Ci][Co][4][4] + bias + addend[src] — last decoder layer
+ *                  forward (models/dcgan_64.py:76); y_dtype = the activation dtype or fp32 (for the skip addend). */
+int p2pvg_conv_thin_in(const void* x, int dtype, const float* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,
+                       void* stream);
+int p2pvg_convT_thin_out(const void* x, int dtype, const float* w, const float* bias, const float* addend, const int* grp_src,
+                         int imgs_per_group, void* y, int y_dtype, int N, int H, int W, int Ci, int Co, void* stream);
+
 /* 4x4 / stride 2 / pad 1 lowering (nn.Conv2d(nin,nout,4,2,1), models/dcgan_64.py:8; and the data-gradient of
  * nn.ConvTranspose2d(nin,nout,4,2,1), models/dcgan_64.py:20): x [N,H,W,C] -> col [N*H/2*W/2, 16*C], K order (kh,kw,c). */
 int p2pvg_im2col_k4s2p1(const void* x, void* col, int dtype, int N, int H, int W, int C, void* stream);

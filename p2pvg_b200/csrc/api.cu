@@ -33,6 +33,9 @@ int p2pvg_gemm_tf32(const void*, long long, const void*, long long, void*, int, 
 int p2pvg_gemm_tc(const void*, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int, const float*,
                   const void*, long long, void*, size_t, cudaStream_t);
 int p2pvg_gemm_tc_available();
+int p2pvg_conv_thin_in_impl(const void*, int, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
+int p2pvg_convT_thin_out_impl(const void*, int, const float*, const float*, const float*, const int*, int, void*, int, int, int, int, int,
+                              int, cudaStream_t);
 int p2pvg_conv_gemm_impl(int, const void*, const void*, long long, void*, int, long long, int, int, int, int, int, int, const float*,
                          const float*, const int*, int, int, void*, size_t, cudaStream_t);
 int p2pvg_im2col_k4s2p1_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
@@ -118,6 +121,15 @@ int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c
   P2PVG_REQUIRE(a && b && c, P2PVG_ERR_BAD_ARG, "conv_gemm: null operand");
   return p2pvg_conv_gemm_impl(kind, a, b, ldb, c, c_dtype, ldc, N, H, W, Ck, Cn, Cm, bias, addend, grp_src, imgs_per_group, accumulate,
                               workspace, ws_bytes, ST);
+}
+
+int p2pvg_conv_thin_in(const void* x, int dtype, const float* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,
+                       void* stream) {
+  return p2pvg_conv_thin_in_impl(x, dtype, w, bias, y, N, H, W, Ci, Co, ST);
+}
+int p2pvg_convT_thin_out(const void* x, int dtype, const float* w, const float* bias, const float* addend, const int* grp_src,
+                         int imgs_per_group, void* y, int y_dtype, int N, int H, int W, int Ci, int Co, void* stream) {
+  return p2pvg_convT_thin_out_impl(x, dtype, w, bias, addend, grp_src, imgs_per_group, y, y_dtype, N, H, W, Ci, Co, ST);
 }
 
 int p2pvg_im2col_k4s2p1(const void* x, void* col, int dtype, int N, int H, int W, int C, void* stream) {

@@ -433,7 +433,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   if (rc) return rc;
   rc = map4d(&tb, b, N, 2 * H, 2 * W, Cn, W, g.bh64, g.bn64, 2);
   if (rc) return rc;
-  const int BN = Cn >= 128 ? 128 : 64;
+  const int BN = 128;  // N = 16*Cn: a 128-wide tile spans two filter taps when Cn == 64
   const int nkb = (int)((pix + 63) / 64);
   const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(16 * Cn, BN);
   int splits = 1;

@@ -148,6 +148,7 @@ class TrainEngine:
         # pixel-box gathers), without im2col / col2im buffers; P2PVG_IMPLICIT=0 keeps the explicit lowering
         import os
         # one persistent cooperative launch per LSTM layer and direction instead of two launches per timestep
+        self.thin = hasattr(kernels, "conv_thin_in") and os.environ.get("P2PVG_THIN", "1") != "0"
         self.fused_scan = hasattr(kernels, "lstm_scan_fwd") and self.R % 64 == 0 and self.R <= 256 and os.environ.get("P2PVG_FUSED_SCAN", "1") != "0"
         self.implicit = (act_dtype == torch.bfloat16) and hasattr(kernels, "conv_gemm") and os.environ.get("P2PVG_IMPLICIT", "1") != "0"
         self.last_plan = None
@@ -380,14 +381,17 @@ class TrainEngine:
             cn, bn = self.enc_names(l)
             imp = self.implicit and cin % 64 == 0 and cout % 64 == 0
             col = None
+            thin = self.thin and cin <= 4
             if imp:
                 K.conv_gemm(0, a, self._packed[f"enc{l}"], raw, N, Ho, Ho, cin, cout, bias=P[cn + ".bias"])
+            elif thin:  # 1/3-channel input: direct HBM-bound kernel on the fp32 master weights
+                K.conv_thin_in(a, P[cn + ".weight"], P[cn + ".bias"], raw, N, H, H, cin, cout)
             else:
                 col = self.buf(f"enc_col{l}", M * 16 * cin)
                 K.im2col(a, col, N, H, H, cin)
                 K.gemm(col, self._packed[f"enc{l}"], raw, M, cout, 16 * cin, bias=P[cn + ".bias"])
             st = self.bn_forward("enc", l, raw, y, T, B * Ho * Ho, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
-            self.enc.append(dict(col=col, raw=raw, y=y, st=st, cin=cin, cout=cout, Hin=H, Hout=Ho, M=M, imp=imp, inp=a))
+            self.enc.append(dict(col=col, raw=raw, y=y, st=st, cin=cin, cout=cout, Hin=H, Hout=Ho, M=M, imp=imp, inp=a, thin=thin))
             a, H = y, Ho
         # final 4x4 valid conv == GEMM over the flattened 4x4xC map
         ctop = self.chans[-1]
@@ -548,13 +552,19 @@ class TrainEngine:
                 addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
                 K.conv_gemm(2, skip, wS, addS, nskip * B, Hi, Hi, cd, cout, bias=P[cn + ".bias"])
                 K.conv_gemm(2, d, wD, raw, N, Hi, Hi, cd, cout, addend=addS, grp_src=self.ix["skip_src"], imgs_per_group=B)
+            elif self.thin and cout <= 3 and cd % 8 == 0:
+                w32 = P[cn + ".weight"]  # [2*cd, nc, 4, 4] fp32 master: rows [0,cd) act on d, rows [cd,2cd) on the skip
+                addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
+                K.convT_thin_out(skip, w32[cd:], P[cn + ".bias"], addS, nskip * B, Hi, Hi, cd, cout)
+                K.convT_thin_out(d, w32[:cd], None, raw, N, Hi, Hi, cd, cout, addend=addS, grp_src=self.ix["skip_src"], imgs_per_group=B)
             else:
                 colD = self.buf("dec_colD", Md * 16 * cout)
                 colS = self.buf("dec_colS", Ms * 16 * cout)
                 K.gemm(d, wD, colD, Md, 16 * cout, cd, b_mn=True)
                 K.gemm(skip, wS, colS, Ms, 16 * cout, cd, b_mn=True)
                 K.col2im(colD, raw, N, Hi, Hi, cout, bias=P[cn + ".bias"], col2=colS, grp_src=self.ix["skip_src"], imgs_per_group=B)
-            rec = dict(inp=d, skip=skip, raw=raw, cd=cd, cout=cout, Hi=Hi, Md=Md, Ms=Ms, imp=imp)
+            rec = dict(inp=d, skip=skip, raw=raw, cd=cd, cout=cout, Hi=Hi, Md=Md, Ms=Ms, imp=imp,
+                       thin=(not imp) and self.thin and cout <= 3 and cd % 8 == 0)
             if k < n - 1:
                 dn = self.buf(f"dec_d{k}", Mo * cout)
                 rec["st"] = self.bn_forward("dec", k, raw, dn, G, B * 4 * Hi * Hi, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
@@ -629,6 +639,23 @@ class TrainEngine:
                     rec["dskip"] = dsk
                     if want_wgrad:
                         K.conv_gemm(1, rec["skip"], dyS, gw[cd * 16 * cout:], nskip * B, Hi, Hi, 0, cout, Cm=cd)
+            elif rec["thin"]:
+                w32 = A.p[cn + ".weight"]
+                K.conv_thin_in(dy, w32[:cd], None, dd, N, Ho, Ho, cout, cd)   # data gradient: the ConvT weight is a conv weight [cd][nc][4][4]
+                if want_wgrad:
+                    dcol = self.buf("scratch_dcol", Md * 16 * cout)
+                    K.im2col(dy, dcol, N, Ho, Ho, cout)
+                    K.gemm(x_in, dcol, gw[:cd * 16 * cout], cd, 16 * cout, Md, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
+                if want_skip:
+                    dyS = self.buf("scratch_dyS", nskip * B * Ho * Ho * cout)
+                    K.group_sum(dy, dyS, self.ix["skip_src"][g0:g1], Gn, nskip, B * Ho * Ho * cout)
+                    dsk = self.buf(f"dskip{k}", Ms * cd)
+                    K.conv_thin_in(dyS, w32[cd:], None, dsk, nskip * B, Ho, Ho, cout, cd)
+                    rec["dskip"] = dsk
+                    if want_wgrad:
+                        dcolS = self.buf("scratch_dcolS", Ms * 16 * cout)
+                        K.im2col(dyS, dcolS, nskip * B, Ho, Ho, cout)
+                        K.gemm(rec["skip"], dcolS, gw[cd * 16 * cout:], cd, 16 * cout, Ms, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
             else:
                 dcol = self.buf("scratch_dcol", Md * 16 * cout)
                 K.im2col(dy, dcol, N, Ho, Ho, cout)
@@ -835,7 +862,11 @@ class TrainEngine:
             if rec["imp"]:
                 K.conv_gemm(1, gy, rec["inp"], gw, N, Ho, Ho, 0, cin, Cm=cout)
             else:
-                K.gemm(gy, rec["col"], gw, cout, 16 * cin, M, a_mn=True, b_mn=True, lda=cout, ldb=16 * cin)
+                col = rec["col"]
+                if col is None:  # thin first layer: the im2col matrix is only needed here
+                    col = self.buf(f"enc_col{l}", M * 16 * cin)
+                    K.im2col(rec["inp"], col, N, rec["Hin"], rec["Hin"], cin)
+                K.gemm(gy, col, gw, cout, 16 * cin, M, a_mn=True, b_mn=True, lda=cout, ldb=16 * cin)
             K.permute4(gw, A.g[cn + ".weight"], (cout, cin, 4, 4), (16 * cin, 1, 4 * cin, cin))
             if l > 0:
                 gprev = self.buf(f"enc_gy{l - 1}", N * rec["Hin"] * rec["Hin"] * cin)
