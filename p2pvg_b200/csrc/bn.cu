@@ -177,36 +177,65 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const T* __restrict__ x, T*
   }
 }
 
+// grid (chunk, group); thread = (channel vector cv, row lane): the per-(group,channel) parameters stay in registers
+// and only the activations stream through.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ sum_dz,
-                                                           const float* __restrict__ sum_dzx, long long R, int C, long long totalv,
+                                                           const float* __restrict__ sum_dzx, long long R, int C, int rows_per_chunk,
                                                            int act, T* __restrict__ dx, const float* __restrict__ scale,
                                                            const float* __restrict__ shift) {
   constexpr int V = VecN<T>::N;
   const int CV = C / V;
-  const float invR = 1.f / (float)R;
+  const int lanes = 256 / CV;
+  const int cv = threadIdx.x % CV, lane = threadIdx.x / CV;
+  const int g = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > R) r1 = R;
   const bool no_y = (y == nullptr);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < totalv; idx += (long long)gridDim.x * blockDim.x) {
-    const uint4 rd = ld_raw16(dy + idx * V), rx = ld_raw16(x + idx * V);
-    const uint4 ry = no_y ? make_uint4(0u, 0u, 0u, 0u) : ld_raw16(y + idx * V);
-    const int cv = (int)(idx % CV);
-    const int g = (int)((idx / CV) / R);
-    float dv[V], xv[V], yv[V], o[V];
-    unpack16<T>(rd, dv);
-    unpack16<T>(rx, xv);
-    unpack16<T>(ry, yv);
+  const float invR = 1.f / (float)R;
+  float mu[V], is[V], k0[V], k1[V], k2[V], sc[V], sh[V];
 #pragma unroll
-    for (int j = 0; j < V; j++) {
-      const long long gc = (long long)g * C + cv * V + j;
-      const float is = invstd[gc];
-      const float xhat = (xv[j] - mean[gc]) * is;
-      const float ya_ = no_y ? fmaf(xv[j], scale[gc], shift[gc]) : yv[j];
-      const float dz = dv[j] * act_grad(ya_, act);
-      o[j] = gamma[cv * V + j] * is * (dz - sum_dz[gc] * invR - xhat * sum_dzx[gc] * invR);
+  for (int j = 0; j < V; j++) {
+    const long long gc = (long long)g * C + cv * V + j;
+    mu[j] = mean[gc];
+    is[j] = invstd[gc];
+    k0[j] = gamma[cv * V + j] * is[j];          // dx = k0 * (dz - k1 - xhat * k2)
+    k1[j] = sum_dz[gc] * invR;
+    k2[j] = sum_dzx[gc] * invR;
+    sc[j] = no_y ? scale[gc] : 0.f;
+    sh[j] = no_y ? shift[gc] : 0.f;
+  }
+  for (long long r = r0 + lane; r < r1; r += 2 * lanes) {
+    const long long off0 = ((long long)g * R + r) * C + cv * V;
+    const bool two = (r + lanes) < r1;
+    const long long off1 = off0 + (long long)lanes * C;
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 da = ld_raw16(dy + off0), xa = ld_raw16(x + off0);
+    const uint4 db = two ? ld_raw16(dy + off1) : z4, xb = two ? ld_raw16(x + off1) : z4;
+    uint4 ya = z4, yb = z4;
+    if (!no_y) {
+      ya = ld_raw16(y + off0);
+      if (two) yb = ld_raw16(y + off1);
     }
-    st_raw16(dx + idx * V, pack16<T>(o));
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (h == 1 && !two) break;
+      float dv[V], xv[V], yv[V], o[V];
+      unpack16<T>(h ? db : da, dv);
+      unpack16<T>(h ? xb : xa, xv);
+      unpack16<T>(h ? yb : ya, yv);
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        const float xhat = (xv[j] - mu[j]) * is[j];
+        const float ya_ = no_y ? fmaf(xv[j], sc[j], sh[j]) : yv[j];
+        const float dz = dv[j] * act_grad(ya_, act);
+        o[j] = k0[j] * (dz - k1[j] - xhat * k2[j]);
+      }
+      st_raw16(dx + (h ? off1 : off0), pack16<T>(o));
+    }
   }
 }
 
@@ -319,9 +348,8 @@ int p2pvg_bn_bwd_impl(const void* dy, const void* x, const void* y, int dtype, c
   DISPATCH_DTYPE(dtype, T, (bn_reduce_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, act, R, C,
                                                                          ch.rows_per_chunk, (double2*)ws, scale, shift)));
   bn_bwd_finalize_kernel<<<cdiv((long long)G * C, 256), 256, 0, st>>>((const double2*)ws, ch.nchunk, G, C, sum_dz, sum_dzx);
-  long long totalv = (long long)G * R * (C / vec);
-  DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<grid_for(totalv, 256), 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, mean, invstd,
-                                                                                          gamma, sum_dz, sum_dzx, R, C, totalv, act, (T*)dx, scale, shift)));
+  DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, mean, invstd, gamma, sum_dz,
+                                                                         sum_dzx, R, C, ch.rows_per_chunk, act, (T*)dx, scale, shift)));
   return p2pvg_check_launch("bn_bwd");
 }
 

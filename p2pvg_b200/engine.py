@@ -148,7 +148,8 @@ class TrainEngine:
         # pixel-box gathers), without im2col / col2im buffers; P2PVG_IMPLICIT=0 keeps the explicit lowering
         import os
         # one persistent cooperative launch per LSTM layer and direction instead of two launches per timestep
-        self.thin = hasattr(kernels, "conv_thin_in") and os.environ.get("P2PVG_THIN", "1") != "0"
+        # direct CUDA-core kernels for the 1/3-channel ends: measured slower than im2col + tcgen05 GEMM, so opt-in only
+        self.thin = hasattr(kernels, "conv_thin_in") and os.environ.get("P2PVG_THIN", "0") == "1"
         self.fused_scan = hasattr(kernels, "lstm_scan_fwd") and self.R % 64 == 0 and self.R <= 256 and os.environ.get("P2PVG_FUSED_SCAN", "1") != "0"
         self.implicit = (act_dtype == torch.bfloat16) and hasattr(kernels, "conv_gemm") and os.environ.get("P2PVG_IMPLICIT", "1") != "0"
         self.last_plan = None

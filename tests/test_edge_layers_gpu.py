@@ -4,6 +4,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False  # the torch reference convolutions must be exact fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope="module")
