@@ -12,44 +12,65 @@
 
 namespace {
 
-template <typename T>
+// thread = (8/4-channel output vector cv, pixel lane): the filter taps of its output channels live in REGISTERS (CI == 1) or are
+// read as float4 from shared memory (CI == 3); per pixel only the 16*CI input samples and one 16-byte store remain.
+template <typename T, int CI>
 __global__ void __launch_bounds__(256) conv_thin_in_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                           T* __restrict__ y, int N, int H, int W, int Ci, int Co) {
+                                                           T* __restrict__ y, int N, int H, int W, int Co) {
   constexpr int V = VecN<T>::N;
-  extern __shared__ float wsm[];  // [16*Ci][Co]  (tap-major, output channel contiguous)
-  const int taps = 16 * Ci;
-  for (int i = threadIdx.x; i < taps * Co; i += blockDim.x) {
-    const int co = i % Co, t = i / Co;       // t = (kh*4+kw)*Ci + ci
-    const int ci = t % Ci, k = t / Ci;
-    wsm[i] = w[((long long)co * Ci + ci) * 16 + k];
+  constexpr int TAPS = 16 * CI;
+  extern __shared__ __align__(16) float wsm[];  // [TAPS][Co]
+  for (int i = threadIdx.x; i < TAPS * Co; i += blockDim.x) {
+    const int co = i % Co, t = i / Co;       // t = (kh*4+kw)*CI + ci
+    const int ci = t % CI, k = t / CI;
+    wsm[i] = w[((long long)co * CI + ci) * 16 + k];
   }
   __syncthreads();
   const int Ho = H >> 1, Wo = W >> 1, CV = Co / V;
-  const long long total = (long long)N * Ho * Wo * CV;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % CV);
-    const long long p = idx / CV;
+  const int cv = threadIdx.x % CV, plane = threadIdx.x / CV, planes = blockDim.x / CV;
+  float wreg[CI == 1 ? TAPS : 1][V];
+  float bv[V];
+#pragma unroll
+  for (int j = 0; j < V; j++) bv[j] = bias ? bias[cv * V + j] : 0.f;
+  if (CI == 1) {
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+#pragma unroll
+      for (int j = 0; j < V; j++) wreg[CI == 1 ? t : 0][j] = wsm[t * Co + cv * V + j];
+  }
+  const long long npix = (long long)N * Ho * Wo;
+  for (long long p = (long long)blockIdx.x * planes + plane; p < npix; p += (long long)gridDim.x * planes) {
     const int ox = (int)(p % Wo);
     const long long t2 = p / Wo;
     const int oy = (int)(t2 % Ho);
     const int n = (int)(t2 / Ho);
     float acc[V];
 #pragma unroll
-    for (int j = 0; j < V; j++) acc[j] = bias ? bias[cv * V + j] : 0.f;
+    for (int j = 0; j < V; j++) acc[j] = bv[j];
 #pragma unroll
     for (int kh = 0; kh < 4; kh++) {
       const int iy = 2 * oy - 1 + kh;
-      if (iy < 0 || iy >= H) continue;
 #pragma unroll
       for (int kw = 0; kw < 4; kw++) {
         const int ix = 2 * ox - 1 + kw;
-        if (ix < 0 || ix >= W) continue;
-        const T* xp = x + (((long long)n * H + iy) * W + ix) * Ci;
-        for (int ci = 0; ci < Ci; ci++) {
-          const float xv = ld_f<T>(xp + ci);
-          const float* wr = wsm + ((kh * 4 + kw) * Ci + ci) * Co + cv * V;
+        const bool ok = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
+        const T* xp = x + (((long long)n * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * CI;
 #pragma unroll
-          for (int j = 0; j < V; j++) acc[j] = fmaf(xv, wr[j], acc[j]);
+        for (int ci = 0; ci < CI; ci++) {
+          const float xv = ok ? ld_f<T>(xp + ci) : 0.f;
+          const int t = (kh * 4 + kw) * CI + ci;
+          if (CI == 1) {
+#pragma unroll
+            for (int j = 0; j < V; j++) acc[j] = fmaf(xv, wreg[CI == 1 ? t : 0][j], acc[j]);
+          } else {
+            const float* wr = wsm + t * Co + cv * V;
+#pragma unroll
+            for (int j = 0; j < V; j += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wr + j);
+              acc[j] = fmaf(xv, w4.x, acc[j]); acc[j + 1] = fmaf(xv, w4.y, acc[j + 1]);
+              acc[j + 2] = fmaf(xv, w4.z, acc[j + 2]); acc[j + 3] = fmaf(xv, w4.w, acc[j + 3]);
+            }
+          }
         }
       }
     }
@@ -57,17 +78,17 @@ __global__ void __launch_bounds__(256) conv_thin_in_kernel(const T* __restrict__
   }
 }
 
-// one thread per output pixel and output channel block; Ci % 8 == 0
-template <typename T, typename TO>
+// one thread per output pixel; CO (1 or 3) output channels held in registers; Ci % 8 == 0; weights read as float4 from smem
+template <typename T, typename TO, int CO>
 __global__ void __launch_bounds__(256) convT_thin_out_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                              const float* __restrict__ addend, const int* __restrict__ grp_src,
-                                                             int imgs_per_group, TO* __restrict__ y, int N, int H, int W, int Ci, int Co) {
+                                                             int imgs_per_group, TO* __restrict__ y, int N, int H, int W, int Ci) {
   constexpr int V = VecN<T>::N;
-  extern __shared__ float wsm[];  // [16][Co][Ci]
-  for (int i = threadIdx.x; i < 16 * Co * Ci; i += blockDim.x) {
+  extern __shared__ __align__(16) float wsm[];  // [16][CO][Ci]
+  for (int i = threadIdx.x; i < 16 * CO * Ci; i += blockDim.x) {
     const int ci = i % Ci, r = i / Ci;
-    const int co = r % Co, k = r / Co;
-    wsm[i] = w[((long long)ci * Co + co) * 16 + k];
+    const int co = r % CO, k = r / CO;
+    wsm[i] = w[((long long)ci * CO + co) * 16 + k];
   }
   __syncthreads();
   const int Ho = 2 * H, Wo = 2 * W;
@@ -77,12 +98,14 @@ __global__ void __launch_bounds__(256) convT_thin_out_kernel(const T* __restrict
     const long long t2 = p / Wo;
     const int oy = (int)(t2 % Ho);
     const int n = (int)(t2 / Ho);
-    float acc[3] = {0.f, 0.f, 0.f};
-    for (int co = 0; co < Co; co++) acc[co] = bias ? bias[co] : 0.f;
+    float acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; co++) acc[co] = bias ? bias[co] : 0.f;
     if (addend) {
       const int n2 = grp_src[n / imgs_per_group] * imgs_per_group + (n % imgs_per_group);
-      const float* ar = addend + (((long long)n2 * Ho + oy) * Wo + ox) * Co;
-      for (int co = 0; co < Co; co++) acc[co] += ar[co];
+      const float* ar = addend + (((long long)n2 * Ho + oy) * Wo + ox) * CO;
+#pragma unroll
+      for (int co = 0; co < CO; co++) acc[co] += ar[co];
     }
     const int kh0 = (oy + 1) & 1, kw0 = (ox + 1) & 1;
 #pragma unroll
@@ -94,21 +117,27 @@ __global__ void __launch_bounds__(256) convT_thin_out_kernel(const T* __restrict
         const int kw = kw0 + 2 * b, tx = ox + 1 - kw, ix = tx >> 1;
         if (tx < 0 || ix >= W) continue;
         const T* xp = x + (((long long)n * H + iy) * W + ix) * Ci;
-        const float* wr = wsm + (kh * 4 + kw) * Co * Ci;
+        const float* wr = wsm + (kh * 4 + kw) * CO * Ci;
         for (int c0 = 0; c0 < Ci; c0 += V) {
           float xv[V];
           unpack16<T>(ld_raw16(xp + c0), xv);
-          for (int co = 0; co < Co; co++) {
-            const float* wc = wr + co * Ci + c0;
-            float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < V; j++) s = fmaf(xv[j], wc[j], s);
-            acc[co] += s;
+          for (int co = 0; co < CO; co++) {
+            const float* wc = wr + co * Ci + c0;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; j += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wc + j);
+              s0 = fmaf(xv[j], w4.x, s0); s1 = fmaf(xv[j + 1], w4.y, s1);
+              s0 = fmaf(xv[j + 2], w4.z, s0); s1 = fmaf(xv[j + 3], w4.w, s1);
+            }
+            acc[co] += s0 + s1;
           }
         }
       }
     }
-    for (int co = 0; co < Co; co++) st_f<TO>(y + p * Co + co, acc[co]);
+#pragma unroll
+    for (int co = 0; co < CO; co++) st_f<TO>(y + p * CO + co, acc[co]);
   }
 }
 
@@ -123,20 +152,27 @@ inline int grid_for(long long total, int block) {
 int p2pvg_conv_thin_in_impl(const void* x, int dtype, const float* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,
                             cudaStream_t st) {
   const int vec = dtype == P2PVG_BF16 ? 8 : 4;
-  P2PVG_REQUIRE(Ci >= 1 && Ci <= 4 && Co % vec == 0 && (H % 2 == 0) && (W % 2 == 0), P2PVG_ERR_UNSUPPORTED,
+  P2PVG_REQUIRE((Ci == 1 || Ci == 3) && Co % vec == 0 && 256 % (Co / vec) == 0 && (H % 2 == 0) && (W % 2 == 0), P2PVG_ERR_UNSUPPORTED,
                 "conv_thin_in: unsupported shape Ci=%d Co=%d %dx%d", Ci, Co, H, W);
   P2PVG_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, P2PVG_ERR_BAD_ARG, "conv_thin_in: output not 16-byte aligned");
   if (N == 0) return P2PVG_OK;
   const size_t smem = (size_t)16 * Ci * Co * sizeof(float);
-  const long long total = (long long)N * (H / 2) * (W / 2) * (Co / vec);
-  DISPATCH_DTYPE(dtype, T, (conv_thin_in_kernel<T><<<grid_for(total, 256), 256, smem, st>>>((const T*)x, w, bias, (T*)y, N, H, W, Ci, Co)));
+  const long long npix = (long long)N * (H / 2) * (W / 2);
+  const int planes = 256 / (Co / vec);
+  long long blocks = (npix + planes - 1) / planes;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (Ci == 1) {
+    DISPATCH_DTYPE(dtype, T, (conv_thin_in_kernel<T, 1><<<(int)blocks, 256, smem, st>>>((const T*)x, w, bias, (T*)y, N, H, W, Co)));
+  } else {
+    DISPATCH_DTYPE(dtype, T, (conv_thin_in_kernel<T, 3><<<(int)blocks, 256, smem, st>>>((const T*)x, w, bias, (T*)y, N, H, W, Co)));
+  }
   return p2pvg_check_launch("conv_thin_in");
 }
 
 int p2pvg_convT_thin_out_impl(const void* x, int dtype, const float* w, const float* bias, const float* addend, const int* grp_src,
                               int imgs_per_group, void* y, int y_dtype, int N, int H, int W, int Ci, int Co, cudaStream_t st) {
   const int vec = dtype == P2PVG_BF16 ? 8 : 4;
-  P2PVG_REQUIRE(Co >= 1 && Co <= 3 && Ci % vec == 0, P2PVG_ERR_UNSUPPORTED, "convT_thin_out: unsupported shape Ci=%d Co=%d", Ci, Co);
+  P2PVG_REQUIRE((Co == 1 || Co == 3) && Ci % vec == 0, P2PVG_ERR_UNSUPPORTED, "convT_thin_out: unsupported shape Ci=%d Co=%d", Ci, Co);
   P2PVG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, P2PVG_ERR_BAD_ARG, "convT_thin_out: input not 16-byte aligned");
   P2PVG_REQUIRE(addend == nullptr || (grp_src != nullptr && imgs_per_group > 0), P2PVG_ERR_BAD_ARG, "convT_thin_out: addend needs grp_src");
   P2PVG_REQUIRE(y_dtype == dtype || y_dtype == P2PVG_F32, P2PVG_ERR_BAD_ARG, "convT_thin_out: output dtype must be the input dtype or fp32");
@@ -145,11 +181,17 @@ int p2pvg_convT_thin_out_impl(const void* x, int dtype, const float* w, const fl
   P2PVG_REQUIRE(smem <= 48 * 1024, P2PVG_ERR_UNSUPPORTED, "convT_thin_out: Ci too large");
   const long long total = (long long)N * 4 * H * W;
   const int grid = grid_for(total, 256);
-  if (dtype == P2PVG_BF16 && y_dtype == P2PVG_BF16)
-    convT_thin_out_kernel<bf16, bf16><<<grid, 256, smem, st>>>((const bf16*)x, w, bias, addend, grp_src, imgs_per_group, (bf16*)y, N, H, W, Ci, Co);
-  else if (dtype == P2PVG_BF16)
-    convT_thin_out_kernel<bf16, float><<<grid, 256, smem, st>>>((const bf16*)x, w, bias, addend, grp_src, imgs_per_group, (float*)y, N, H, W, Ci, Co);
-  else
-    convT_thin_out_kernel<float, float><<<grid, 256, smem, st>>>((const float*)x, w, bias, addend, grp_src, imgs_per_group, (float*)y, N, H, W, Ci, Co);
+#define LAUNCH(TI, TO, CO_) \
+  convT_thin_out_kernel<TI, TO, CO_><<<grid, 256, smem, st>>>((const TI*)x, w, bias, addend, grp_src, imgs_per_group, (TO*)y, N, H, W, Ci)
+  if (Co == 1) {
+    if (dtype == P2PVG_BF16 && y_dtype == P2PVG_BF16) LAUNCH(bf16, bf16, 1);
+    else if (dtype == P2PVG_BF16) LAUNCH(bf16, float, 1);
+    else LAUNCH(float, float, 1);
+  } else {
+    if (dtype == P2PVG_BF16 && y_dtype == P2PVG_BF16) LAUNCH(bf16, bf16, 3);
+    else if (dtype == P2PVG_BF16) LAUNCH(bf16, float, 3);
+    else LAUNCH(float, float, 3);
+  }
+#undef LAUNCH
   return p2pvg_check_launch("convT_thin_out");
 }
