@@ -142,29 +142,37 @@ __global__ void bn_bwd_finalize_kernel(const double2* __restrict__ partial, int 
   sum_dzx[idx] = (float)b;
 }
 
+// grid (chunk, group); thread = (channel vector cv, row lane); scale / shift of the thread's channels stay in registers
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
-                                                     const float* __restrict__ shift, long long R, int C, long long totalv, int act) {
+                                                     const float* __restrict__ shift, long long R, int C, int rows_per_chunk, int act) {
   constexpr int V = VecN<T>::N;
   const int CV = C / V;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < totalv; base += 2 * stride) {
-    uint4 raw[2];
+  const int lanes = 256 / CV;
+  const int cv = threadIdx.x % CV, lane = threadIdx.x / CV;
+  const int g = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > R) r1 = R;
+  float sc[V], sh[V];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const long long idx = base + u * stride;
-      if (idx < totalv) raw[u] = ld_raw16(x + idx * V);
+  for (int j = 0; j < V; j++) {
+    sc[j] = scale[(long long)g * C + cv * V + j];
+    sh[j] = shift[(long long)g * C + cv * V + j];
+  }
+  for (long long r = r0 + lane; r < r1; r += 4 * lanes) {
+    uint4 raw[4];
+    long long off[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      off[u] = ((long long)g * R + r + (long long)u * lanes) * C + cv * V;
+      if (r + (long long)u * lanes < r1) raw[u] = ld_raw16(x + off[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const long long idx = base + u * stride;
-      if (idx >= totalv) continue;
-      const int cv = (int)(idx % CV);
-      const int g = (int)((idx / CV) / R);
+    for (int u = 0; u < 4; u++) {
+      if (r + (long long)u * lanes >= r1) break;
       float v[V];
       unpack16<T>(raw[u], v);
-      const float* sc = scale + (long long)g * C + cv * V;
-      const float* sh = shift + (long long)g * C + cv * V;
 #pragma unroll
       for (int j = 0; j < V; j++) {
         float z = fmaf(v[j], sc[j], sh[j]);
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const T* __restrict__ x, T*
         else if (act == P2PVG_ACT_TANH) z = tanhf(z);
         v[j] = z;
       }
-      st_raw16(y + idx * V, pack16<T>(v));
+      st_raw16(y + off[u], pack16<T>(v));
     }
   }
 }
@@ -276,7 +284,7 @@ __global__ void bn_ema_kernel(float* __restrict__ rmean, float* __restrict__ rva
   rvar[c] = v;
 }
 
-inline int grid_for(long long total, int block) {
+__attribute__((unused)) inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 64;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -327,10 +335,11 @@ int p2pvg_bn_fwd_stats_impl(const void* x, int dtype, int G, long long R, int C,
 int p2pvg_bn_act_impl(const void* x, void* y, int dtype, const float* scale, const float* shift, int G, long long R, int C, int act,
                       cudaStream_t st) {
   const int vec = dtype == P2PVG_BF16 ? 8 : 4;
-  P2PVG_REQUIRE(C % vec == 0, P2PVG_ERR_UNSUPPORTED, "bn_act: C not a multiple of the 16-byte vector");
-  long long totalv = (long long)G * R * (C / vec);
-  if (totalv == 0) return P2PVG_OK;
-  DISPATCH_DTYPE(dtype, T, (bn_act_kernel<T><<<grid_for((totalv + 1) / 2, 256), 256, 0, st>>>((const T*)x, (T*)y, scale, shift, R, C, totalv, act)));
+  if (int e = check_bn_shape(C, vec, "bn_act")) return e;
+  if (G == 0 || R == 0) return P2PVG_OK;
+  Chunking ch = choose_chunks(R, C, vec);
+  dim3 grid(ch.nchunk, G);
+  DISPATCH_DTYPE(dtype, T, (bn_act_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (T*)y, scale, shift, R, C, ch.rows_per_chunk, act)));
   return p2pvg_check_launch("bn_act");
 }
 
