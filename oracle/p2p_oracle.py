@@ -116,6 +116,60 @@ def _dcgan_decoder_container(g_dim, nc, width):
     return m
 
 
+def _residual_linear_container(nin, nout):
+    """models/h36m_mlp.py:28-43 — shortcut Linear+ReLU, long path of three Linear+ReLU (hidden nin//2), LayerNorm."""
+    nn = torch.nn
+    m = nn.Module()
+    m.shortcut = nn.Sequential(nn.Linear(nin, nout), nn.ReLU())
+    m.long_path = nn.Sequential(nn.Linear(nin, nin // 2), nn.ReLU(), nn.Linear(nin // 2, nin // 2), nn.ReLU(),
+                                nn.Linear(nin // 2, nout), nn.ReLU())
+    m.norm = nn.LayerNorm(nout)
+    return m
+
+
+def _mlp_encoder_container(in_dim, out_dim, h_dim):
+    nn = torch.nn
+    m = nn.Module()
+    m.fc1 = _residual_linear_container(in_dim, h_dim)
+    m.fc2 = _residual_linear_container(h_dim, h_dim)
+    m.fc3 = nn.Linear(h_dim, out_dim)
+    return m
+
+
+def _mlp_decoder_container(in_dim, out_dim, h_dim):
+    nn = torch.nn
+    m = nn.Module()
+    m.fc1 = _residual_linear_container(in_dim, h_dim)
+    m.fc2 = _residual_linear_container(h_dim * 2, h_dim)
+    m.fc3 = nn.Linear(h_dim * 2, out_dim)
+    return m
+
+
+def residual_linear_fwd(p, pre, x):
+    """models/h36m_mlp.py:45-46."""
+    sc = F.relu(F.linear(x, p[pre + ".shortcut.0.weight"], p[pre + ".shortcut.0.bias"]))
+    h = x
+    for i in (0, 2, 4):
+        h = F.relu(F.linear(h, p[pre + f".long_path.{i}.weight"], p[pre + f".long_path.{i}.bias"]))
+    s = sc + h
+    return F.layer_norm(s, (s.shape[-1],), p[pre + ".norm.weight"], p[pre + ".norm.bias"], 1e-5)
+
+
+def mlp_encoder_fwd(p, x):
+    """models/h36m_mlp.py:61-69 — x [B,17,3]; returns (latent [B,g], [h1, h2])."""
+    h1 = residual_linear_fwd(p, "fc1", x.reshape(x.shape[0], -1))
+    h2 = residual_linear_fwd(p, "fc2", h1)
+    return torch.tanh(F.linear(h2, p["fc3.weight"], p["fc3.bias"])), [h1, h2]
+
+
+def mlp_decoder_fwd(p, vec, skips):
+    """models/h36m_mlp.py:85-95."""
+    d1 = residual_linear_fwd(p, "fc1", vec)
+    d2 = residual_linear_fwd(p, "fc2", torch.cat([d1, skips[1]], 1))
+    out = F.linear(torch.cat([d2, skips[0]], 1), p["fc3.weight"], p["fc3.bias"])
+    return out.reshape(out.shape[0], 17, 3)
+
+
 def build_state(cfg: dict, seed: int | None = None, dtype=torch.float32) -> "OrderedDict[str, OrderedDict]":
     """Initial parameters + buffers of the five modules.
 
@@ -124,12 +178,17 @@ def build_state(cfg: dict, seed: int | None = None, dtype=torch.float32) -> "Ord
     """
     if seed is not None:
         torch.manual_seed(seed)
-    g, z, r, nc, w = cfg["g_dim"], cfg["z_dim"], cfg["rnn_size"], cfg["channels"], cfg["image_width"]
+    g, z, r = cfg["g_dim"], cfg["z_dim"], cfg["rnn_size"]
     fp = _lstm_container(g + z + 2, g, r, cfg.get("predictor_rnn_layers", 2), gaussian=False)
     post = _lstm_container(2 * g + 2, z, r, cfg.get("posterior_rnn_layers", 1), gaussian=True)
     prior = _lstm_container(2 * g + 2, z, r, cfg.get("prior_rnn_layers", 1), gaussian=True)
-    enc = _dcgan_encoder_container(g, nc, w)
-    dec = _dcgan_decoder_container(g, nc, w)
+    if cfg.get("backbone", "dcgan") == "mlp":  # models/p2p_model.py:33-35 (h36m)
+        enc = _mlp_encoder_container(51, g, g)
+        dec = _mlp_decoder_container(g, 51, g)
+    else:
+        nc, w = cfg["channels"], cfg["image_width"]
+        enc = _dcgan_encoder_container(g, nc, w)
+        dec = _dcgan_decoder_container(g, nc, w)
     mods = OrderedDict(frame_predictor=fp, posterior=post, prior=prior, encoder=enc, decoder=dec)
     for m in mods.values():
         m.apply(_init_weights_like_reference)
@@ -305,11 +364,16 @@ def forward_losses(state, x, opt, width, eps, probs, tape=None):
     """
     enc, dec = state["encoder"], state["decoder"]
     fp, post, prior = state["frame_predictor"], state["posterior"], state["prior"]
+    if width == "mlp":  # h36m pose backbone: x [T,B,17,3]
+        encoder_fwd_ = lambda p, xx, w: mlp_encoder_fwd(p, xx)
+        decoder_fwd_ = lambda p, v, sk, w: mlp_decoder_fwd(p, v, sk)
+    else:
+        encoder_fwd_, decoder_fwd_ = encoder_fwd, decoder_fwd
     seq_len, B = x.shape[0], x.shape[1]
     cp_ix = seq_len - 1
     hid_fp, hid_post, hid_prior = init_hidden(fp, B, x), init_hidden(post, B, x), init_hidden(prior, B, x)
     x_cp = x[cp_ix]
-    global_z = encoder_fwd(enc, x_cp, width)[0]  # p2p_model.py:71-78, not detached
+    global_z = encoder_fwd_(enc, x_cp, width)[0]  # p2p_model.py:71-78, not detached
     sched = skip_schedule(seq_len, probs, opt["skip_prob"], opt["n_past"])
     mse = kld = cpc = align = 0
     h = h_pred = skip = None
@@ -319,8 +383,8 @@ def forward_losses(state, x, opt, width, eps, probs, tape=None):
             align = align + F.mse_loss(h[0].expand_as(h_pred), h_pred)
         t_tuc = x.new_zeros(B, 1).fill_(tuc)
         t_dt = x.new_zeros(B, 1).fill_(dt)
-        h_full = encoder_fwd(enc, x[i - 1], width)
-        h_target = encoder_fwd(enc, x[i], width)[0]
+        h_full = encoder_fwd_(enc, x[i - 1], width)
+        h_target = encoder_fwd_(enc, x[i], width)[0]
         if opt["last_frame_skip"] or i <= opt["n_past"]:
             h, skip = h_full
         else:
@@ -330,10 +394,10 @@ def forward_losses(state, x, opt, width, eps, probs, tape=None):
         zt, mu, logvar = gaussian_lstm_fwd(post, hid_post, h_target_cpaw, eps[s, 0])
         zt_p, mu_p, logvar_p = gaussian_lstm_fwd(prior, hid_prior, h_cpaw, eps[s, 1])
         h_pred = lstm_fwd(fp, hid_fp, torch.cat([h, zt, t_tuc, t_dt], 1))
-        x_pred = decoder_fwd(dec, h_pred, skip, width)
+        x_pred = decoder_fwd_(dec, h_pred, skip, width)
         if i == cp_ix:
             h_pred_p = lstm_fwd(fp, hid_fp, torch.cat([h, zt_p, t_tuc, t_dt], 1))
-            x_pred_p = decoder_fwd(dec, h_pred_p, skip, width)
+            x_pred_p = decoder_fwd_(dec, h_pred_p, skip, width)
             cpc = F.mse_loss(x_pred_p, x_cp)
         mse = mse + F.mse_loss(x_pred, x[i])
         kld = kld + kl_criterion(mu, logvar, mu_p, logvar_p, opt["batch_size"])

@@ -84,8 +84,10 @@ def import_reference():
     backbones = {}
     import models.dcgan_64 as d64
     import models.dcgan_128 as d128
+    import models.h36m_mlp as mlp
     backbones[64] = d64
     backbones[128] = d128
+    backbones["mlp"] = mlp
     return p2p_model, backbones
 
 
@@ -106,6 +108,8 @@ CASES = {
     "d128_plain": dict(width=128, channels=3, T=4, B=2, steps=1, opt={}, np_seed=1),
     # configured batch_size != runtime batch: KL divides by the configured one (misc/criterion.py:15)
     "d64_cfgbatch": dict(width=64, channels=1, T=4, B=2, steps=1, opt=dict(batch_size=5), np_seed=2),
+    # human3.6m pose backbone (models/h36m_mlp.py): x is the tuple (pose_2d, pose_3d, camera_view), MSE on [B,17,3]
+    "h36m_mlp": dict(width="mlp", channels=1, T=7, B=4, steps=1, opt=dict(dataset="h36m", skip_prob=0.3), np_seed=4),
 }
 
 
@@ -123,7 +127,7 @@ def run_case(name, spec, p2p_model, backbones):
                 encoder=model.encoder, decoder=model.decoder)
     fix = dict(case=name, cfg=dict(g_dim=g_dim, z_dim=z_dim, rnn_size=rnn, channels=spec["channels"],
                                    image_width=spec["width"], predictor_rnn_layers=2, posterior_rnn_layers=1,
-                                   prior_rnn_layers=1),
+                                   prior_rnn_layers=1, backbone=("mlp" if spec["width"] == "mlp" else "dcgan")),
                opt={k: getattr(opt, k) for k in ("beta", "weight_cpc", "weight_align", "skip_prob", "n_past",
                                                  "last_frame_skip", "lr", "beta1", "batch_size")},
                init_seed=1, torch=torch.__version__)
@@ -151,7 +155,7 @@ def run_case(name, spec, p2p_model, backbones):
     gen = torch.Generator().manual_seed(1234 + len(name))
     for step in range(spec["steps"]):
         T, B, C, W = spec["T"], spec["B"], spec["channels"], spec["width"]
-        x = torch.rand(T, B, C, W, W, generator=gen)
+        x = torch.randn(T, B, 17, 3, generator=gen) if W == "mlp" else torch.rand(T, B, C, W, W, generator=gen)
         np.random.seed(spec["np_seed"] + step)
         probs = np.random.uniform(0, 1, T - 1)
         np.random.seed(spec["np_seed"] + step)  # forward() redraws the same vector
@@ -169,7 +173,7 @@ def run_case(name, spec, p2p_model, backbones):
 
         model.update_model_without_prior = snap_then_update
         model.zero_grad()
-        losses = model(x, 0, T - 1)
+        losses = model((None, x, None) if W == "mlp" else x, 0, T - 1)
         model.update_model_without_prior = orig_update
         n_exec = sum(1 for r in tape if r["m"] == "posterior")
         torch.manual_seed(eps_seed)
