@@ -35,6 +35,7 @@ extern "C" {
 #define P2PVG_ACT_NONE 0
 #define P2PVG_ACT_LRELU 1 /* LeakyReLU(0.2): models/dcgan_64.py:10,22 */
 #define P2PVG_ACT_TANH 2  /* models/dcgan_64.py:45, models/lstm.py:18 */
+#define P2PVG_ACT_RELU 4   /* models/h36m_mlp.py:33-41 */
 #define P2PVG_ACT_SIGMOID 3 /* models/dcgan_64.py:77 (stand-alone decoder forward; act_fwd only) */
 
 int p2pvg_version(void);
@@ -156,6 +157,15 @@ int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act
 int p2pvg_mse_chunks(void);
 int p2pvg_sigmoid_mse(const void* raw, int dtype, const float* x, const int* tgt, const float* coef, int G, int64_t E,
                       void* pred, void* d_raw, float* partial, void* stream);
+/* h36m pose backbone (models/h36m_mlp.py): nn.LayerNorm of residual_linear (:43,46) forward / backward (fp32, row-wise; dx may alias
+ * dy; dgamma == NULL skips the parameter gradients) and the plain nn.MSELoss on [B,17,3] poses (models/p2p_model.py:254,256) with
+ * the same partial-sum layout as p2pvg_sigmoid_mse. */
+int p2pvg_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows, int C,
+                        float eps, void* stream);
+int p2pvg_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,
+                        float* dgamma, float* dbeta, int64_t rows, int C, void* ws, size_t ws_bytes, void* stream);
+int p2pvg_mse_plain(const float* pred, const float* x, const int* tgt, const float* coef, int G, int64_t E, float* d_pred, float* partial,
+                    void* stream);
 /* the four scalars returned by P2PModel.forward (models/p2p_model.py:271): out[0..3] = mse,kld,cpc,align (/seq_len). */
 int p2pvg_finalize_losses(const float* mse_partial, int n_recon, int has_cpc, double E, const float* kl_sum, float batch_size,
                           const float* align_partial, int n_align, float seq_len, float* out, void* stream);

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libp2pvg_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 
 _lib = None
 
@@ -239,6 +239,17 @@ class CudaKernels:
     def sigmoid_mse(self, raw, x, tgt, coef, G, E, pred, d_raw, partial):
         self._ck(self.lib.p2pvg_sigmoid_mse(_p(raw), _i(_dt(raw)), _p(x), _p(tgt), _p(coef), _i(G), _i64(E), _p(pred), _p(d_raw),
                                             _p(partial), self._stream()))
+
+    def layernorm_fwd(self, x, gamma, beta, y, mean, rstd, rows, C, eps=1e-5):
+        self._ck(self.lib.p2pvg_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _i64(rows), _i(C), _f(eps), self._stream()))
+
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, C):
+        ws = self.bn_workspace(1, 1)
+        self._ck(self.lib.p2pvg_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma), _p(dbeta), _i64(rows), _i(C),
+                                              _p(ws), _sz(ws.numel()), self._stream()))
+
+    def mse_plain(self, pred, x, tgt, coef, G, E, d_pred, partial):
+        self._ck(self.lib.p2pvg_mse_plain(_p(pred), _p(x), _p(tgt), _p(coef), _i(G), _i64(E), _p(d_pred), _p(partial), self._stream()))
 
     def finalize_losses(self, mse_partial, n_recon, has_cpc, E, kl_sum, batch_size, align_partial, n_align, seq_len, out):
         self._ck(self.lib.p2pvg_finalize_losses(_p(mse_partial), _i(n_recon), _i(int(has_cpc)), _d(float(E)), _p(kl_sum),

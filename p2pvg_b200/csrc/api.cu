@@ -33,6 +33,10 @@ int p2pvg_gemm_tf32(const void*, long long, const void*, long long, void*, int, 
 int p2pvg_gemm_tc(const void*, int, long long, const void*, int, long long, void*, int, long long, int, int, int, int, const float*,
                   const void*, long long, void*, size_t, cudaStream_t);
 int p2pvg_gemm_tc_available();
+int p2pvg_layernorm_fwd_impl(const float*, const float*, const float*, float*, float*, float*, long long, int, float, cudaStream_t);
+int p2pvg_layernorm_bwd_impl(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, long long, int,
+                             void*, size_t, cudaStream_t);
+int p2pvg_mse_plain_impl(const float*, const float*, const int*, const float*, int, long long, float*, float*, int, cudaStream_t);
 int p2pvg_conv_thin_in_impl(const void*, int, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
 int p2pvg_convT_thin_out_impl(const void*, int, const float*, const float*, const float*, const int*, int, void*, int, int, int, int, int,
                               int, cudaStream_t);
@@ -220,6 +224,18 @@ int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act
   return p2pvg_act_bwd_impl(dy, y, dx, n, act, ST);
 }
 int p2pvg_mse_chunks(void) { return p2pvg_mse_chunks_impl(); }
+int p2pvg_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows, int C,
+                        float eps, void* stream) {
+  return p2pvg_layernorm_fwd_impl(x, gamma, beta, y, mean, rstd, rows, C, eps, ST);
+}
+int p2pvg_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,
+                        float* dgamma, float* dbeta, int64_t rows, int C, void* ws, size_t ws_bytes, void* stream) {
+  return p2pvg_layernorm_bwd_impl(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, C, ws, ws_bytes, ST);
+}
+int p2pvg_mse_plain(const float* pred, const float* x, const int* tgt, const float* coef, int G, int64_t E, float* d_pred, float* partial,
+                    void* stream) {
+  return p2pvg_mse_plain_impl(pred, x, tgt, coef, G, E, d_pred, partial, p2pvg_mse_chunks_impl(), ST);
+}
 int p2pvg_sigmoid_mse(const void* raw, int dtype, const float* x, const int* tgt, const float* coef, int G, int64_t E,
                       void* pred, void* d_raw, float* partial, void* stream) {
   return p2pvg_sigmoid_mse_impl(raw, dtype, x, tgt, coef, G, E, pred, d_raw, partial, ST);

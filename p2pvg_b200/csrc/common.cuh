@@ -18,6 +18,7 @@
 #define P2PVG_ACT_LRELU 1
 #define P2PVG_ACT_TANH 2
 #define P2PVG_ACT_SIGMOID 3
+#define P2PVG_ACT_RELU 4
 
 // thread-local error string (C ABI: p2pvg_last_error)
 void p2pvg_set_error(const char* fmt, ...);

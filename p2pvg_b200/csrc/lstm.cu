@@ -194,6 +194,7 @@ __global__ void act_fwd_kernel(float* __restrict__ x, long long n, int act) {
     if (act == P2PVG_ACT_TANH) v = tanhf(v);
     else if (act == P2PVG_ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
     else if (act == P2PVG_ACT_SIGMOID) v = sigmoidf_(v);
+    else if (act == P2PVG_ACT_RELU) v = fmaxf(v, 0.f);
     x[i] = v;
   }
 }
@@ -202,6 +203,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
     float yv = y[i], g = 1.f;
     if (act == P2PVG_ACT_TANH) g = 1.f - yv * yv;
     else if (act == P2PVG_ACT_LRELU) g = yv > 0.f ? 1.f : 0.2f;
+    else if (act == P2PVG_ACT_RELU) g = yv > 0.f ? 1.f : 0.f;
     dx[i] = dy[i] * g;
   }
 }
