@@ -128,11 +128,16 @@ class TrainEngine:
         self.adt = act_dtype
         self.mode = mode
         self.g, self.z, self.R = cfg["g_dim"], cfg["z_dim"], cfg["rnn_size"]
-        self.nc, self.W0 = cfg["channels"], cfg["image_width"]
-        self.chans = [64, 128, 256, 512] if self.W0 == 64 else [64, 128, 256, 512, 512]
-        if self.W0 not in (64, 128):
-            raise ValueError("dcgan backbones exist for 64 and 128 pixel frames")
-        self.n = len(self.chans)
+        self.backbone = cfg.get("backbone", "dcgan")
+        if self.backbone == "dcgan":
+            self.nc, self.W0 = cfg["channels"], cfg["image_width"]
+            self.chans = [64, 128, 256, 512] if self.W0 == 64 else [64, 128, 256, 512, 512]
+            if self.W0 not in (64, 128):
+                raise ValueError("dcgan backbones exist for 64 and 128 pixel frames")
+            self.n = len(self.chans)
+            self.frame_elems = self.nc * self.W0 * self.W0
+        else:
+            self.frame_elems = 51  # h36m pose: 17 joints x 3
         self.arena, self.buffers = {}, {}
         for m in ("frame_predictor", "posterior", "prior", "encoder", "decoder"):
             params = OrderedDict((k, v) for k, v in state[m].items() if is_param_key(k))
@@ -262,7 +267,7 @@ class TrainEngine:
         fl[:2 * S1].copy_(plan.f_host.reshape(-1), non_blocking=True)
         self.ix = {k: ints[o:o + ln] for k, (o, ln) in plan.int_layout.items()}
         self.tuc, self.dt = fl[:S1], fl[S1:2 * S1]
-        E = self.nc * self.W0 * self.W0
+        E = self.frame_elems
         coef = [1.0 / (self.B * E)] * plan.S + [self.opt["weight_cpc"] / (self.B * E)]
         cf = self.fbuf("plan_coef", 256)
         cf[:S1].copy_(torch.tensor(coef, dtype=torch.float64).float(), non_blocking=True)
@@ -787,7 +792,7 @@ class TrainEngine:
                 self.d_hpred, self.dH)
         # the four scalars
         self.loss_out = self.fbuf("loss_out", 4)
-        E = B * self.nc * self.W0 * self.W0
+        E = B * self.frame_elems
         K.finalize_losses(self.mse_partial, S, plan.has_cpc, E, self.kl_sum, float(opt["batch_size"]), self.align_partial,
                           max(S - 1, 0), float(T), self.loss_out)
         # frame predictor (recon steps only; the CPC step has no cotangent in this pass)

@@ -211,8 +211,8 @@ def p2p_generate(model, x, len_output, eval_cp_ix, model_mode="full", skip_frame
     """Autoregressive point-to-point generation (reference models/p2p_model.py:80-183): one sample per input
     sequence; skipped frames are emitted as zeros; posterior sees ground truth only while it exists."""
     opt = model.opt
-    if isinstance(x, tuple):
-        raise NotImplementedError("h36m tuple input is not part of this build yet")
+    if isinstance(x, tuple):  # h36m
+        x = x[1]
     batch_size = x[0].shape[0]
     gen_seq = [x[0]]
     x_in = x[0]
@@ -257,3 +257,49 @@ def p2p_generate(model, x, len_output, eval_cp_ix, model_mode="full", skip_frame
             x_in = model.decoder([h_pred, skip])
             gen_seq.append(x_in)
     return gen_seq
+
+
+# ---- human3.6m pose backbone (reference models/h36m_mlp.py:45-46, 61-69, 85-95) -----------------------------------------
+def _linear(K, lin, x, rows, act=None):
+    out = torch.empty(rows, lin.out_features, device=x.device)
+    K.gemm(x, lin.weight.data, out, rows, lin.out_features, lin.in_features, bias=lin.bias.data)
+    if act is not None:
+        K.act_fwd(out, out.numel(), act)
+    return out
+
+
+def _residual_linear(K, rl, x, rows):
+    from ._lib import ACT_RELU
+    sc = _linear(K, rl.shortcut[0], x, rows, ACT_RELU)
+    h = x
+    for i in (0, 2, 4):
+        h = _linear(K, rl.long_path[i], h, rows, ACT_RELU)
+    K.permute4(h, sc, (sc.numel(), 1, 1, 1), (1, 0, 0, 0), accumulate=True)
+    n = rl.norm.normalized_shape[0]
+    y = torch.empty_like(sc)
+    mean, rstd = torch.empty(rows, device=x.device), torch.empty(rows, device=x.device)
+    K.layernorm_fwd(sc, rl.norm.weight.data, rl.norm.bias.data, y, mean, rstd, rows, n)
+    return y
+
+
+@torch.no_grad()
+def mlp_encoder_forward(mod, x):
+    K = kernels_for(x.device)
+    K.set_fp32_gemm_mode(0)
+    B = int(x.shape[0])
+    xf = x.reshape(B, -1).float().contiguous()
+    h1 = _residual_linear(K, mod.fc1, xf, B)
+    h2 = _residual_linear(K, mod.fc2, h1, B)
+    return _linear(K, mod.fc3, h2, B, ACT_TANH), [h1, h2]
+
+
+@torch.no_grad()
+def mlp_decoder_forward(mod, vec, skip):
+    K = kernels_for(vec.device)
+    K.set_fp32_gemm_mode(0)
+    vec = vec.float().contiguous()
+    B = int(vec.shape[0])
+    d1 = _residual_linear(K, mod.fc1, vec, B)
+    d2 = _residual_linear(K, mod.fc2, torch.cat([d1, skip[1].float()], 1).contiguous(), B)
+    out = _linear(K, mod.fc3, torch.cat([d2, skip[0].float()], 1).contiguous(), B)
+    return out.view(B, 17, 3)

@@ -78,10 +78,13 @@ class P2PModel(nn.Module):
         self.frame_predictor = lstm_models.lstm(g_dim + z_dim + 2, g_dim, rnn_size, predictor_rnn_layers, batch_size)
         self.posterior = lstm_models.gaussian_lstm(2 * g_dim + 2, z_dim, rnn_size, posterior_rnn_layers, batch_size)
         self.prior = lstm_models.gaussian_lstm(2 * g_dim + 2, z_dim, rnn_size, prior_rnn_layers, batch_size)
-        if getattr(opt, "dataset", None) == "h36m":
-            raise NotImplementedError("h36m_mlp backbone is not part of this build yet (SURVEY.md §8 row a8)")
-        self.encoder = opt.backbone_net.encoder(g_dim, channels)
-        self.decoder = opt.backbone_net.decoder(g_dim, channels)
+        self.is_pose = getattr(opt, "dataset", None) == "h36m"
+        if self.is_pose:  # models/p2p_model.py:33-35
+            self.encoder = opt.backbone_net.encoder(out_dim=g_dim, h_dim=g_dim)
+            self.decoder = opt.backbone_net.decoder(in_dim=g_dim, h_dim=g_dim)
+        else:
+            self.encoder = opt.backbone_net.encoder(g_dim, channels)
+            self.decoder = opt.backbone_net.decoder(g_dim, channels)
         opt.optimizer = ArenaAdam
         self.mse_criterion = nn.MSELoss()
         self.kl_criterion = criterion.KLCriterion(opt=opt)
@@ -129,13 +132,16 @@ class P2PModel(nn.Module):
             return self._engine
         from .._lib import CudaKernels
         from ..engine import TrainEngine
+        from ..engine_mlp import TrainEngineMLP
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("p2pvg_b200 has no CPU path: move the model to a CUDA device first (model.cuda())")
-        cfg = dict(g_dim=self.g_dim, z_dim=self.z_dim, rnn_size=self.rnn_size, channels=self.channels, image_width=width)
+        cfg = dict(g_dim=self.g_dim, z_dim=self.z_dim, rnn_size=self.rnn_size, channels=self.channels, image_width=width,
+                   backbone="mlp" if self.is_pose else "dcgan")
         state = {m: getattr(self, m).state_dict() for m in MODULES}
         adt = torch.float32 if self.precision == "fp32" else torch.bfloat16
-        eng = TrainEngine(state, cfg, self._opt_dict(), CudaKernels(dev), act_dtype=adt, mode=self.update_mode)
+        cls = TrainEngineMLP if self.is_pose else TrainEngine
+        eng = cls(state, cfg, self._opt_dict(), CudaKernels(dev), act_dtype=adt, mode=self.update_mode)
         for m in MODULES:
             mod = getattr(self, m)
             named = list(mod.named_parameters())
@@ -152,8 +158,8 @@ class P2PModel(nn.Module):
     def forward(self, x, start_ix=0, cp_ix=-1):
         """One training step; returns (mse, kld, cpc, align) numpy scalars divided by seq_len
         (reference models/p2p_model.py:185-271)."""
-        if isinstance(x, tuple):
-            raise NotImplementedError("h36m tuple input is not part of this build yet")
+        if isinstance(x, tuple):  # h36m: (pose_2d, pose_3d, camera_view) -> pose_3d (models/p2p_model.py:187-189)
+            x = x[1]
         if not torch.is_tensor(x):
             x = torch.stack(list(x))
         eng = self.engine(int(x.shape[-1]))

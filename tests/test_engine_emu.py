@@ -46,13 +46,14 @@ def bn_cancelled_bias(m, k):
     return False
 
 
-def compare(ref, got, eng, state, rtol_loss=1e-4, rtol_grad=2e-3, lr=1e-3):
+def compare(ref, got, eng, state, rtol_loss=1e-4, rtol_grad=2e-3, lr=1e-3, cancelled=None):
+    bn_cancelled = cancelled if cancelled is not None else bn_cancelled_bias
     np.testing.assert_allclose(got, np.array(ref["losses"], dtype=np.float32), rtol=rtol_loss, atol=1e-7)
     for m in O.MODULES:
         gmax = max(g.abs().max().item() for g in ref["grads"][m].values())
         for k, gref in ref["grads"][m].items():
             g = eng.arena[m].g[k]
-            if bn_cancelled_bias(m, k):
+            if bn_cancelled(m, k):
                 assert g.abs().max().item() <= 1e-4 * gmax, f"grad {m}.{k} should be ~0"
                 continue
             scale = gref.abs().max().item() + 1e-12
@@ -70,7 +71,7 @@ def compare(ref, got, eng, state, rtol_loss=1e-4, rtol_grad=2e-3, lr=1e-3):
                 assert dw.max().item() <= 2.2 * lr, f"weight {m}.{k}"
                 gref = ref["grads"][m][k]
                 solid = gref.abs() > 3e-2 * (gref.abs().max() + 1e-30)
-                if not bn_cancelled_bias(m, k) and solid.any():
+                if not bn_cancelled(m, k) and solid.any():
                     assert dw[solid].max().item() <= 2e-5 + 0.1 * lr, f"weight {m}.{k}: {dw[solid].max().item():.3e}"
             elif v.is_floating_point():
                 assert torch.allclose(eng.buffers[m][k], v, rtol=1e-4, atol=1e-6), f"buffer {m}.{k}"
