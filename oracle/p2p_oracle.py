@@ -116,6 +116,70 @@ def _dcgan_decoder_container(g_dim, nc, width):
     return m
 
 
+VGG_ENC = [[(None, 64), (64, 64)], [(64, 128), (128, 128)], [(128, 256), (256, 256), (256, 256)], [(256, 512), (512, 512), (512, 512)]]
+VGG_DEC = [[(1024, 512), (512, 512), (512, 256)], [(512, 256), (256, 256), (256, 128)], [(256, 128), (128, 64)], [(128, 64)]]
+
+
+def _vgg_layer(nin, nout):
+    nn = torch.nn
+    blk = nn.Module()
+    blk.main = nn.Sequential(nn.Conv2d(nin, nout, 3, 1, 1), nn.BatchNorm2d(nout), nn.LeakyReLU(LRELU))
+    return blk
+
+
+def _vgg_encoder_container(g_dim, nc):
+    """models/vgg_64.py:16-48."""
+    nn = torch.nn
+    m = nn.Module()
+    for i, stage in enumerate(VGG_ENC, 1):
+        setattr(m, f"c{i}", nn.Sequential(*[_vgg_layer(nc if a is None else a, b) for a, b in stage]))
+    m.c5 = nn.Sequential(nn.Conv2d(512, g_dim, 4, 1, 0), nn.BatchNorm2d(g_dim), nn.Tanh())
+    return m
+
+
+def _vgg_decoder_container(g_dim, nc):
+    """models/vgg_64.py:59-92."""
+    nn = torch.nn
+    m = nn.Module()
+    m.upc1 = nn.Sequential(nn.ConvTranspose2d(g_dim, 512, 4, 1, 0), nn.BatchNorm2d(512), nn.LeakyReLU(LRELU))
+    for i, stage in enumerate(VGG_DEC[:3], 2):
+        setattr(m, f"upc{i}", nn.Sequential(*[_vgg_layer(a, b) for a, b in stage]))
+    m.upc5 = nn.Sequential(_vgg_layer(128, 64), nn.ConvTranspose2d(64, nc, 3, 1, 1), nn.Sigmoid())
+    return m
+
+
+def _vgg_block(p, pre, x, training=True):
+    x = F.conv2d(x, p[pre + ".main.0.weight"], p[pre + ".main.0.bias"], stride=1, padding=1)
+    return F.leaky_relu(_bn_train(x, p, pre + ".main.1", training), LRELU)
+
+
+def vgg_encoder_fwd(p, x, training=True):
+    """models/vgg_64.py:50-56."""
+    skips, h = [], x
+    for i, stage in enumerate(VGG_ENC, 1):
+        if i > 1:
+            h = F.max_pool2d(h, 2, 2)
+        for j in range(len(stage)):
+            h = _vgg_block(p, f"c{i}.{j}", h, training)
+        skips.append(h)
+    h = F.conv2d(F.max_pool2d(h, 2, 2), p["c5.0.weight"], p["c5.0.bias"])
+    h = torch.tanh(_bn_train(h, p, "c5.1", training))
+    return h.reshape(h.shape[0], -1), skips
+
+
+def vgg_decoder_fwd(p, vec, skips, training=True):
+    """models/vgg_64.py:94-105."""
+    d = F.conv_transpose2d(vec.reshape(vec.shape[0], -1, 1, 1), p["upc1.0.weight"], p["upc1.0.bias"])
+    d = F.leaky_relu(_bn_train(d, p, "upc1.1", training), LRELU)
+    for i, stage in enumerate(VGG_DEC[:3], 2):
+        d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skips[5 - i]], 1)
+        for j in range(len(stage)):
+            d = _vgg_block(p, f"upc{i}.{j}", d, training)
+    d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skips[0]], 1)
+    d = _vgg_block(p, "upc5.0", d, training)
+    return torch.sigmoid(F.conv_transpose2d(d, p["upc5.1.weight"], p["upc5.1.bias"], stride=1, padding=1))
+
+
 def _residual_linear_container(nin, nout):
     """models/h36m_mlp.py:28-43 — shortcut Linear+ReLU, long path of three Linear+ReLU (hidden nin//2), LayerNorm."""
     nn = torch.nn
@@ -185,6 +249,9 @@ def build_state(cfg: dict, seed: int | None = None, dtype=torch.float32) -> "Ord
     if cfg.get("backbone", "dcgan") == "mlp":  # models/p2p_model.py:33-35 (h36m)
         enc = _mlp_encoder_container(51, g, g)
         dec = _mlp_decoder_container(g, 51, g)
+    elif cfg.get("backbone") == "vgg":
+        enc = _vgg_encoder_container(g, cfg["channels"])
+        dec = _vgg_decoder_container(g, cfg["channels"])
     else:
         nc, w = cfg["channels"], cfg["image_width"]
         enc = _dcgan_encoder_container(g, nc, w)
@@ -367,6 +434,9 @@ def forward_losses(state, x, opt, width, eps, probs, tape=None):
     if width == "mlp":  # h36m pose backbone: x [T,B,17,3]
         encoder_fwd_ = lambda p, xx, w: mlp_encoder_fwd(p, xx)
         decoder_fwd_ = lambda p, v, sk, w: mlp_decoder_fwd(p, v, sk)
+    elif width == "vgg":
+        encoder_fwd_ = lambda p, xx, w: vgg_encoder_fwd(p, xx)
+        decoder_fwd_ = lambda p, v, sk, w: vgg_decoder_fwd(p, v, sk)
     else:
         encoder_fwd_, decoder_fwd_ = encoder_fwd, decoder_fwd
     seq_len, B = x.shape[0], x.shape[1]

@@ -85,9 +85,11 @@ def import_reference():
     import models.dcgan_64 as d64
     import models.dcgan_128 as d128
     import models.h36m_mlp as mlp
+    import models.vgg_64 as vgg64
     backbones[64] = d64
     backbones[128] = d128
     backbones["mlp"] = mlp
+    backbones["vgg"] = vgg64
     return p2p_model, backbones
 
 
@@ -108,6 +110,8 @@ CASES = {
     "d128_plain": dict(width=128, channels=3, T=4, B=2, steps=1, opt={}, np_seed=1),
     # configured batch_size != runtime batch: KL divides by the configured one (misc/criterion.py:15)
     "d64_cfgbatch": dict(width=64, channels=1, T=4, B=2, steps=1, opt=dict(batch_size=5), np_seed=2),
+    # vgg_64 backbone (models/vgg_64.py), 3-channel frames (weizmann shape)
+    "vgg64_rgb": dict(width="vgg", channels=3, T=4, B=2, steps=1, opt={}, np_seed=6),
     # human3.6m pose backbone (models/h36m_mlp.py): x is the tuple (pose_2d, pose_3d, camera_view), MSE on [B,17,3]
     "h36m_mlp": dict(width="mlp", channels=1, T=7, B=4, steps=1, opt=dict(dataset="h36m", skip_prob=0.3), np_seed=4),
 }
@@ -127,7 +131,7 @@ def run_case(name, spec, p2p_model, backbones):
                 encoder=model.encoder, decoder=model.decoder)
     fix = dict(case=name, cfg=dict(g_dim=g_dim, z_dim=z_dim, rnn_size=rnn, channels=spec["channels"],
                                    image_width=spec["width"], predictor_rnn_layers=2, posterior_rnn_layers=1,
-                                   prior_rnn_layers=1, backbone=("mlp" if spec["width"] == "mlp" else "dcgan")),
+                                   prior_rnn_layers=1, backbone=(spec["width"] if spec["width"] in ("mlp", "vgg") else "dcgan")),
                opt={k: getattr(opt, k) for k in ("beta", "weight_cpc", "weight_align", "skip_prob", "n_past",
                                                  "last_frame_skip", "lr", "beta1", "batch_size")},
                init_seed=1, torch=torch.__version__)
@@ -155,7 +159,11 @@ def run_case(name, spec, p2p_model, backbones):
     gen = torch.Generator().manual_seed(1234 + len(name))
     for step in range(spec["steps"]):
         T, B, C, W = spec["T"], spec["B"], spec["channels"], spec["width"]
-        x = torch.randn(T, B, 17, 3, generator=gen) if W == "mlp" else torch.rand(T, B, C, W, W, generator=gen)
+        if W == "mlp":
+            x = torch.randn(T, B, 17, 3, generator=gen)
+        else:
+            side = 64 if W == "vgg" else W
+            x = torch.rand(T, B, C, side, side, generator=gen)
         np.random.seed(spec["np_seed"] + step)
         probs = np.random.uniform(0, 1, T - 1)
         np.random.seed(spec["np_seed"] + step)  # forward() redraws the same vector
