@@ -67,10 +67,31 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
  *           and the Conv2d data-gradient; `addend` (fp32, big-map layout) is the skip half of torch.cat([d, skip], 1)
  *           (models/dcgan_64.py:84-87) computed once per distinct source call; image n adds addend image
  *           grp_src[n / imgs_per_group] * imgs_per_group + n % imgs_per_group.
+ * 3x3 / stride-1 / pad-1 variants for the vgg_64 layers (models/vgg_64.py:8-13), both maps H x W:
+ *   kind 3: c[N,H,W,Cn] = conv3x3(a[N,H,W,Ck]) . b[Cn,(kh,kw,Ck)] + bias + addend[src]       forward; `addend` (fp32 [.,H,W,Cn])
+ *           is the skip half of torch.cat([up(d), skip], 1) (models/vgg_64.py:97-104), indexed like kind 2
+ *   kind 4: c[Cm,(kh,kw,Cn)] = sum_pix a[pix,Cm]^T . gather_3x3(b[N,H,W,Cn])                  weight gradient (fp32)
+ *   kind 5: kind 3 with mirrored tap offsets, b = [Cin,(kh,kw,Cout)]                          data gradient
  * Returns P2PVG_ERR_UNSUPPORTED for shapes outside the pixel-box tiling (channels not a multiple of 64, ...). */
 int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c, int c_dtype, int64_t ldc, int N, int H, int W, int Ck,
                     int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
                     void* workspace, size_t ws_bytes, void* stream);
+
+/* vgg_64 data movement (models/vgg_64.py), NHWC, dtype f32 | bf16.
+ *   im2col3  : col[(n,y,x), tap*C + c] = x[n, y + sgn*(kh-1), x + sgn*(kw-1), c], row pitch ld >= 9C (pad columns zeroed);
+ *              explicit lowering of nn.Conv2d(.,.,3,1,1) (models/vgg_64.py:9) for the fp32 path and the 3-channel ends
+ *   col2im3  : y[(n,y,x), c] = bias[c] + sum_tap col[(n, y-(kh-1), x-(kw-1)), tap*C + c]   nn.ConvTranspose2d(64,nc,3,1,1)
+ *              (models/vgg_64.py:88) after the [pix,64] x [64,9*nc] GEMM
+ *   maxpool2 : nn.MaxPool2d(2,2) (models/vgg_64.py:47) forward / backward (first maximum in row-major order takes the gradient)
+ *   upsample2: nn.UpsamplingNearest2d(scale_factor=2) (models/vgg_64.py:91) forward / backward
+ *   gather_add: dst[g] += src_f32[grp_src[g]] over chunks of n elements (skip-half addend, explicit path). */
+int p2pvg_im2col3(const void* x, void* col, int dtype, int N, int H, int W, int C, int ld, int sgn, void* stream);
+int p2pvg_col2im3(const void* col, void* y, int dtype, int N, int H, int W, int C, int ld, const float* bias, void* stream);
+int p2pvg_maxpool2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int p2pvg_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int H, int W, int C, void* stream);
+int p2pvg_upsample2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int p2pvg_upsample2_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, void* stream);
+int p2pvg_gather_add(void* dst, int dtype, const float* src, const int* grp_src, int G, int64_t n, void* stream);
 
 /* Thin ends of the dcgan stacks (1 or 3 image channels on one side; HBM-bound direct kernels, fp32 master weights):
  *   conv_thin_in : y[N,H/2,W/2,Co] = conv4x4/s2/p1(x[N,H,W,Ci<=4]) . w[Co][Ci][4][4] + bias   — encoder c1 forward

@@ -122,10 +122,11 @@ class CudaKernels:
     def conv_gemm(self, kind, a, b, c, N, H, W, Ck, Cn, Cm=0, ldb=None, ldc=None, bias=None, addend=None, grp_src=None,
                   imgs_per_group=0, accumulate=False):
         """kind 0/1/2 of p2pvg_conv_gemm (see include/p2pvg_b200.h).  H, W: small-map size."""
+        taps = 9 if kind >= 3 else 16
         if ldb is None:
-            ldb = 16 * Ck if kind == 0 else 16 * Cn
+            ldb = taps * Ck if kind in (0, 3, 5) else taps * Cn
         if ldc is None:
-            ldc = 16 * Cn if kind == 1 else Cn
+            ldc = taps * Cn if kind in (1, 4) else Cn
         ws = self.gemm_workspace()
         self._ck(self.lib.p2pvg_conv_gemm(_i(kind), _p(a), _p(b), _i64(ldb), _p(c), _i(_dt(c)), _i64(ldc), _i(N), _i(H), _i(W), _i(Ck),
                                           _i(Cn), _i(Cm), _p(bias), _p(addend), _p(grp_src), _i(imgs_per_group), _i(int(accumulate)),
@@ -145,6 +146,27 @@ class CudaKernels:
     def col2im(self, col, y, N, Hi, Wi, C, bias=None, col2=None, grp_src=None, imgs_per_group=0, accumulate=False):
         self._ck(self.lib.p2pvg_col2im_k4s2p1(_p(col), _p(col2), _p(grp_src), _i(imgs_per_group), _p(y), _i(_dt(col)), _i(N),
                                               _i(Hi), _i(Wi), _i(C), _p(bias), _i(int(accumulate)), self._stream()))
+
+    def im2col3(self, x, col, N, H, W, C, ld, sgn=1):
+        self._ck(self.lib.p2pvg_im2col3(_p(x), _p(col), _i(_dt(x)), _i(N), _i(H), _i(W), _i(C), _i(ld), _i(sgn), self._stream()))
+
+    def col2im3(self, col, y, N, H, W, C, ld, bias=None):
+        self._ck(self.lib.p2pvg_col2im3(_p(col), _p(y), _i(_dt(col)), _i(N), _i(H), _i(W), _i(C), _i(ld), _p(bias), self._stream()))
+
+    def maxpool2_fwd(self, x, y, N, H, W, C):
+        self._ck(self.lib.p2pvg_maxpool2_fwd(_p(x), _p(y), _i(_dt(x)), _i(N), _i(H), _i(W), _i(C), self._stream()))
+
+    def maxpool2_bwd(self, x, dy, dx, N, H, W, C):
+        self._ck(self.lib.p2pvg_maxpool2_bwd(_p(x), _p(dy), _p(dx), _i(_dt(x)), _i(N), _i(H), _i(W), _i(C), self._stream()))
+
+    def upsample2_fwd(self, x, y, N, H, W, C):
+        self._ck(self.lib.p2pvg_upsample2_fwd(_p(x), _p(y), _i(_dt(x)), _i(N), _i(H), _i(W), _i(C), self._stream()))
+
+    def upsample2_bwd(self, dy, dx, N, H, W, C):
+        self._ck(self.lib.p2pvg_upsample2_bwd(_p(dy), _p(dx), _i(_dt(dy)), _i(N), _i(H), _i(W), _i(C), self._stream()))
+
+    def gather_add(self, dst, src, grp_src, G, n):
+        self._ck(self.lib.p2pvg_gather_add(_p(dst), _i(_dt(dst)), _p(src), _p(grp_src), _i(G), _i64(n), self._stream()))
 
     def permute4(self, src, dst, dims, strides, accumulate=False):
         d = (_i * 4)(*dims)

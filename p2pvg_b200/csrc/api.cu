@@ -43,6 +43,13 @@ int p2pvg_convT_thin_out_impl(const void*, int, const float*, const float*, cons
 int p2pvg_conv_gemm_impl(int, const void*, const void*, long long, void*, int, long long, int, int, int, int, int, int, const float*,
                          const float*, const int*, int, int, void*, size_t, cudaStream_t);
 int p2pvg_im2col_k4s2p1_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
+int p2pvg_im2col3_impl(const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int p2pvg_col2im3_impl(const void*, void*, int, int, int, int, int, int, const float*, cudaStream_t);
+int p2pvg_maxpool2_fwd_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
+int p2pvg_maxpool2_bwd_impl(const void*, const void*, void*, int, int, int, int, int, cudaStream_t);
+int p2pvg_upsample2_fwd_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
+int p2pvg_upsample2_bwd_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
+int p2pvg_gather_add_impl(void*, int, const float*, const int*, int, long long, cudaStream_t);
 int p2pvg_col2im_k4s2p1_impl(const void*, const void*, const int*, int, void*, int, int, int, int, int, const float*, int, cudaStream_t);
 int p2pvg_permute4_impl(const void*, int, void*, int, const int*, const long long*, int, cudaStream_t);
 int p2pvg_add_indexed_impl(void*, const void*, int, const int*, int, long long, cudaStream_t);
@@ -149,6 +156,27 @@ int p2pvg_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, con
 }
 int p2pvg_add_indexed(void* dst, const void* src, int dtype, const int* dst_idx, int F, int64_t n, void* stream) {
   return p2pvg_add_indexed_impl(dst, src, dtype, dst_idx, F, n, ST);
+}
+int p2pvg_im2col3(const void* x, void* col, int dtype, int N, int H, int W, int C, int ld, int sgn, void* stream) {
+  return p2pvg_im2col3_impl(x, col, dtype, N, H, W, C, ld, sgn, ST);
+}
+int p2pvg_col2im3(const void* col, void* y, int dtype, int N, int H, int W, int C, int ld, const float* bias, void* stream) {
+  return p2pvg_col2im3_impl(col, y, dtype, N, H, W, C, ld, bias, ST);
+}
+int p2pvg_maxpool2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
+  return p2pvg_maxpool2_fwd_impl(x, y, dtype, N, H, W, C, ST);
+}
+int p2pvg_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int H, int W, int C, void* stream) {
+  return p2pvg_maxpool2_bwd_impl(x, dy, dx, dtype, N, H, W, C, ST);
+}
+int p2pvg_upsample2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
+  return p2pvg_upsample2_fwd_impl(x, y, dtype, N, H, W, C, ST);
+}
+int p2pvg_upsample2_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, void* stream) {
+  return p2pvg_upsample2_bwd_impl(dy, dx, dtype, N, H, W, C, ST);
+}
+int p2pvg_gather_add(void* dst, int dtype, const float* src, const int* grp_src, int G, int64_t n, void* stream) {
+  return p2pvg_gather_add_impl(dst, dtype, src, grp_src, G, n, ST);
 }
 int p2pvg_group_sum(const void* in, void* out, int dtype, const int* grp_src, int G, int F, int64_t n, void* stream) {
   return p2pvg_group_sum_impl(in, out, dtype, grp_src, G, F, n, ST);

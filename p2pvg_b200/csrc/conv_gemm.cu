@@ -12,6 +12,9 @@
 // kind 2  y_big[N,2H,2W,Cn] = convT_s2(x_small[N,H,W,Ck]) . W[Ck, (tap, Cn)] + bias + addend   ConvT forward, Conv data-gradient
 //         (4 output-parity phases, each a 2x2 stride-1 convolution; `addend` holds the skip-connection half of
 //          torch.cat([d, skip]) computed once per distinct source call and is indexed through grp_src)
+// kind 3  y[N,H,W,Cn] = conv3x3_s1_p1(x[N,H,W,Ck]) . W[Cn, (tap, Ck)] + bias + addend      vgg layer forward (kind 0 geometry, 9 taps)
+// kind 4  g[Cm, (tap, Cn)] = sum_pix a[pix, Cm]^T . gather_3x3(b)[pix, tap, Cn]             vgg weight gradients (kind 1 geometry)
+// kind 5  kind 3 with mirrored tap offsets (pixel - (kh-1, kw-1)): the data gradient of a 3x3 convolution
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -38,7 +41,8 @@ struct Geom {
   int Ntot;             // GEMM N: kind 0/2: Cn; kind 1: 16*Cn
   int bh128, bn128;     // pixel box of 128 pixels: {W, bh128, bn128}
   int bh64, bn64;       // pixel box of 64 pixels (kind 1 K-blocks)
-  int imgs_per_group;   // kind 2 addend indexing
+  int imgs_per_group;   // addend indexing
+  int ks, st, sgn;      // filter taps per side (4 | 3), stride between the two maps (2 | 1), tap-offset sign (+1 | -1)
 };
 
 __device__ __forceinline__ void pix_block(int pb, int P, int H, int W, int bh, int bn, int& n0, int& y0) {
@@ -77,7 +81,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_tiles = tiles_mn * splits * phases;
   const int cchunks = g.Ck / 64;
   // K blocks: kind 0: 16 taps x Ck/64; kind 2: 4 taps x Ck/64; kind 1: pixel blocks of 64
-  const int nkb_total = (KIND == 0) ? 16 * cchunks : (KIND == 2) ? 4 * cchunks : (g.N * g.H * g.W + 63) / 64;
+  const int nkb_total = (KIND == 0) ? g.ks * g.ks * cchunks : (KIND == 2) ? 4 * cchunks : (g.N * g.H * g.W + 63) / 64;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C_::STAGES; s++) {
@@ -123,7 +127,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
           if (KIND == 0) {
             const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * 64;
-            tma_load_4d(&tmA, &full_bar[s], sa, c0, (tap & 3) - 1, 2 * py0 + (tap >> 2) - 1, pn0);
+            const int kh = tap / g.ks, kw = tap - kh * g.ks;
+            tma_load_4d(&tmA, &full_bar[s], sa, c0, g.sgn * (kw - 1), g.st * py0 + g.sgn * (kh - 1), pn0);
             tma_load_2d(&tmB, &full_bar[s], sb, tap * g.Ck + c0, n0);
           } else if (KIND == 2) {
             const int tq = kb / cchunks, c0 = (kb - tq * cchunks) * 64;
@@ -145,7 +150,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int q = 0; q < BN / 64; q++) {
               const int nb = n0 + 64 * q;
               const int tap = nb / g.Cn, c0 = nb - tap * g.Cn;
-              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, c0, (tap & 3) - 1, 2 * ky0 + (tap >> 2) - 1, kn0);
+              const int kh = tap / g.ks, kw = tap - kh * g.ks;
+              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, c0, kw - 1, g.st * ky0 + kh - 1, kn0);
             }
           }
         }
@@ -216,6 +222,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           add_row = ((long long)n2 * (2 * g.H) + oy) * (2 * g.W) + ox;
         }
       }
+      if (KIND == 0 && addend && row_ok) {
+        const int HW = g.H * g.W;
+        const int n = (int)(out_row / HW);
+        const int n2 = grp_src[n / g.imgs_per_group] * g.imgs_per_group + (n % g.imgs_per_group);
+        add_row = (long long)n2 * HW + (out_row - (long long)n * HW);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -238,7 +250,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; j++) f[j] += bias[nbase + j];
         }
-        if (KIND == 2 && addend) {
+        if (KIND != 1 && addend) {
           const float* ar = addend + add_row * g.Ntot + nbase;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -388,10 +400,14 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
                          int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
   std::call_once(g_once2, resolve2);
   P2PVG_REQUIRE(g_enc != nullptr, P2PVG_ERR_UNSUPPORTED, "conv_gemm: cuTensorMapEncodeTiled unavailable");
-  P2PVG_REQUIRE(kind >= 0 && kind <= 2, P2PVG_ERR_BAD_ARG, "conv_gemm: bad kind %d", kind);
+  P2PVG_REQUIRE(kind >= 0 && kind <= 5, P2PVG_ERR_BAD_ARG, "conv_gemm: bad kind %d", kind);
   if (N <= 0) return P2PVG_OK;
   Geom g;
   g.N = N; g.H = H; g.W = W; g.Ck = Ck; g.Cn = Cn; g.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : 1;
+  g.ks = kind >= 3 ? 3 : 4; g.st = kind >= 3 ? 1 : 2; g.sgn = kind == 5 ? -1 : 1;
+  const int taps = g.ks * g.ks;
+  if (kind == 3 || kind == 5) kind = 0;
+  if (kind == 4) kind = 1;
   bool ok = box_for(128, H, W, g.bh128, g.bn128) && box_for(64, H, W, g.bh64, g.bn64);
   ok = ok && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
   if (kind == 1) ok = ok && (Cn % 64 == 0) && (Cm % 8 == 0);
@@ -406,14 +422,14 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   const long long pix = (long long)N * H * W;
   if (kind == 0) {
     g.M = (int)pix; g.Ntot = Cn;
-    rc = map4d(&ta, a, N, 2 * H, 2 * W, Ck, W, g.bh128, g.bn128, 2);
+    rc = map4d(&ta, a, N, g.st * H, g.st * W, Ck, W, g.bh128, g.bn128, g.st);
     if (rc) return rc;
     const int BN = Cn > 64 ? 128 : 64;
-    rc = map2d(&tb, b, 16LL * Ck, Cn, ldb, BN);
+    rc = map2d(&tb, b, (long long)taps * Ck, Cn, ldb, BN);
     if (rc) return rc;
-    const int nkb = 16 * (Ck / 64);
-    if (BN == 128) return launch<0, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, nullptr, nullptr, nullptr, 1, nkb, st);
-    return launch<0, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, nullptr, nullptr, nullptr, 1, nkb, st);
+    const int nkb = taps * (Ck / 64);
+    if (BN == 128) return launch<0, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
+    return launch<0, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
   }
   if (kind == 2) {
     g.M = (int)pix; g.Ntot = Cn;
@@ -428,20 +444,20 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   }
   // kind 1: weight gradient
   P2PVG_REQUIRE(c_dtype == P2PVG_F32, P2PVG_ERR_BAD_ARG, "conv_gemm kind 1 writes fp32");
-  g.M = Cm; g.Ntot = 16 * Cn; g.Ck = 64;
+  g.M = Cm; g.Ntot = taps * Cn; g.Ck = 64;
   rc = map2d(&ta, a, Cm, pix, Cm, 64);  // a_small [pix][Cm] as MN-major A
   if (rc) return rc;
-  rc = map4d(&tb, b, N, 2 * H, 2 * W, Cn, W, g.bh64, g.bn64, 2);
+  rc = map4d(&tb, b, N, g.st * H, g.st * W, Cn, W, g.bh64, g.bn64, g.st);
   if (rc) return rc;
-  const int BN = 128;  // N = 16*Cn: a 128-wide tile spans two filter taps when Cn == 64
+  const int BN = (g.Ntot % 128 == 0) ? 128 : 64;  // a 128-wide tile spans two filter taps when Cn == 64
   const int nkb = (int)((pix + 63) / 64);
-  const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(16 * Cn, BN);
+  const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(g.Ntot, BN);
   int splits = 1;
   if (tiles < 120 && nkb >= 16) {
     long long want = (2 * g_sms + tiles - 1) / tiles, maxs = nkb / 8;
     splits = (int)(want < maxs ? want : maxs);
     if (splits < 1) splits = 1;
-    while (splits > 1 && (ws == nullptr || (size_t)splits * Cm * 16 * Cn * sizeof(float) > ws_bytes)) splits /= 2;
+    while (splits > 1 && (ws == nullptr || (size_t)splits * Cm * g.Ntot * sizeof(float) > ws_bytes)) splits /= 2;
   }
   int kbps = cdiv(nkb, splits);
   splits = cdiv(nkb, kbps);
@@ -450,9 +466,9 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   else rc = launch<1, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
   if (rc) return rc;
   if (splits > 1) {
-    long long total = (long long)Cm * 16 * Cn;
+    long long total = (long long)Cm * g.Ntot;
     int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
-    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, (float*)c, ldc, Cm, 16 * Cn, accumulate);
+    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, (float*)c, ldc, Cm, g.Ntot, accumulate);
     return p2pvg_check_launch("conv_splitk_reduce");
   }
   return P2PVG_OK;

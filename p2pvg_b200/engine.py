@@ -129,8 +129,10 @@ class TrainEngine:
         self.mode = mode
         self.g, self.z, self.R = cfg["g_dim"], cfg["z_dim"], cfg["rnn_size"]
         self.backbone = cfg.get("backbone", "dcgan")
-        if self.backbone == "dcgan":
+        if self.backbone in ("dcgan", "vgg"):
             self.nc, self.W0 = cfg["channels"], cfg["image_width"]
+            if self.backbone == "vgg":
+                self.W0 = 64  # models/vgg_64.py is 64x64 only
             self.chans = [64, 128, 256, 512] if self.W0 == 64 else [64, 128, 256, 512, 512]
             if self.W0 not in (64, 128):
                 raise ValueError("dcgan backbones exist for 64 and 128 pixel frames")

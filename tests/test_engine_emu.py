@@ -46,7 +46,7 @@ def bn_cancelled_bias(m, k):
     return False
 
 
-def compare(ref, got, eng, state, rtol_loss=1e-4, rtol_grad=2e-3, lr=1e-3, cancelled=None):
+def compare(ref, got, eng, state, rtol_loss=1e-4, rtol_grad=2e-3, lr=1e-3, cancelled=None, cos_tol=1e-5, buf_atol=1e-6, max_bad_frac=0.0):
     bn_cancelled = cancelled if cancelled is not None else bn_cancelled_bias
     np.testing.assert_allclose(got, np.array(ref["losses"], dtype=np.float32), rtol=rtol_loss, atol=1e-7)
     for m in O.MODULES:
@@ -57,11 +57,12 @@ def compare(ref, got, eng, state, rtol_loss=1e-4, rtol_grad=2e-3, lr=1e-3, cance
                 assert g.abs().max().item() <= 1e-4 * gmax, f"grad {m}.{k} should be ~0"
                 continue
             scale = gref.abs().max().item() + 1e-12
-            err = (g - gref).abs().max().item()
+            bad = ((g - gref).abs() > 10 * rtol_grad * scale).float().mean().item()
+            err = (g - gref).abs().max().item() if bad > max_bad_frac else 0.0
             cos = torch.nn.functional.cosine_similarity(g.flatten().double(), gref.flatten().double(), dim=0).item()
             # BatchNorm makes many weight gradients sums of nearly cancelling terms: judge direction tightly
             # (cosine) and the worst element loosely
-            assert cos >= 1 - 1e-5 and err <= 10 * rtol_grad * scale, f"grad {m}.{k}: cos {cos:.8f} err {err:.3e} scale {scale:.3e}"
+            assert cos >= 1 - cos_tol and err <= 10 * rtol_grad * scale, f"grad {m}.{k}: cos {cos:.8f} err {err:.3e} scale {scale:.3e}"
         for k, v in state[m].items():
             if O.is_param(k):
                 w = eng.arena[m].p[k]
@@ -72,9 +73,9 @@ def compare(ref, got, eng, state, rtol_loss=1e-4, rtol_grad=2e-3, lr=1e-3, cance
                 gref = ref["grads"][m][k]
                 solid = gref.abs() > 3e-2 * (gref.abs().max() + 1e-30)
                 if not bn_cancelled(m, k) and solid.any():
-                    assert dw[solid].max().item() <= 2e-5 + 0.1 * lr, f"weight {m}.{k}: {dw[solid].max().item():.3e}"
+                    assert (dw[solid] > 2e-5 + 0.1 * lr).float().mean().item() <= max_bad_frac, f"weight {m}.{k}: {dw[solid].max().item():.3e}"
             elif v.is_floating_point():
-                assert torch.allclose(eng.buffers[m][k], v, rtol=1e-4, atol=1e-6), f"buffer {m}.{k}"
+                assert torch.allclose(eng.buffers[m][k], v, rtol=1e-4, atol=buf_atol), f"buffer {m}.{k}"
             else:
                 assert torch.equal(eng.buffers[m][k], v), f"buffer {m}.{k}"
 
