@@ -133,14 +133,15 @@ class P2PModel(nn.Module):
         from .._lib import CudaKernels
         from ..engine import TrainEngine
         from ..engine_mlp import TrainEngineMLP
+        from ..engine_vgg import TrainEngineVGG
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("p2pvg_b200 has no CPU path: move the model to a CUDA device first (model.cuda())")
         cfg = dict(g_dim=self.g_dim, z_dim=self.z_dim, rnn_size=self.rnn_size, channels=self.channels, image_width=width,
-                   backbone="mlp" if self.is_pose else "dcgan")
+                   backbone="mlp" if self.is_pose else getattr(self.encoder, "backbone", "dcgan"))
         state = {m: getattr(self, m).state_dict() for m in MODULES}
         adt = torch.float32 if self.precision == "fp32" else torch.bfloat16
-        cls = TrainEngineMLP if self.is_pose else TrainEngine
+        cls = {"mlp": TrainEngineMLP, "vgg": TrainEngineVGG}.get(cfg["backbone"], TrainEngine)
         eng = cls(state, cfg, self._opt_dict(), CudaKernels(dev), act_dtype=adt, mode=self.update_mode)
         for m in MODULES:
             mod = getattr(self, m)

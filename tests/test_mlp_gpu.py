@@ -68,7 +68,7 @@ def run_step(optkw, T, B, precision, np_seed=0):
     return ref, got, eng
 
 
-@pytest.mark.parametrize("precision,rtol,mincos", [("fp32", 1e-4, 1 - 1e-5), ("bf16", 1e-2, 0.995)])
+@pytest.mark.parametrize("precision,rtol,mincos", [("fp32", 1e-4, 1 - 1e-5), ("bf16", 1e-2, 0.98)])
 @pytest.mark.parametrize("optkw,T,B,seed", [({}, 6, 5, 0), (dict(skip_prob=0.5, n_past=2, last_frame_skip=True), 9, 3, 3)])
 def test_mlp_step_vs_oracle(precision, rtol, mincos, optkw, T, B, seed):
     ref, got, eng = run_step(optkw, T, B, precision, seed)
