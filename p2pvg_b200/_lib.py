@@ -176,6 +176,9 @@ class CudaKernels:
     def add_indexed(self, dst, src, dst_idx, F, n):
         self._ck(self.lib.p2pvg_add_indexed(_p(dst), _p(src), _i(_dt(dst)), _p(dst_idx), _i(F), _i64(n), self._stream()))
 
+    def blockdiag(self, src, dst, R, C, g):
+        self._ck(self.lib.p2pvg_blockdiag(_p(src), _i(_dt(src)), _p(dst), _i(_dt(dst)), _i(R), _i(C), _i(g), self._stream()))
+
     def group_sum(self, inp, out, grp_src, G, F, n):
         self._ck(self.lib.p2pvg_group_sum(_p(inp), _p(out), _i(_dt(inp)), _p(grp_src), _i(G), _i(F), _i64(n), self._stream()))
 

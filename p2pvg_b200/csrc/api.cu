@@ -54,6 +54,7 @@ int p2pvg_col2im_k4s2p1_impl(const void*, const void*, const int*, int, void*, i
 int p2pvg_permute4_impl(const void*, int, void*, int, const int*, const long long*, int, cudaStream_t);
 int p2pvg_add_indexed_impl(void*, const void*, int, const int*, int, long long, cudaStream_t);
 int p2pvg_group_sum_impl(const void*, void*, int, const int*, int, int, long long, cudaStream_t);
+int p2pvg_blockdiag_impl(const void*, int, void*, int, int, int, int, cudaStream_t);
 size_t p2pvg_bn_workspace_bytes_impl(int, int);
 int p2pvg_bn_fwd_stats_impl(const void*, int, int, long long, int, const float*, const float*, float, void*, size_t, float*, float*,
                             float*, float*, float*, cudaStream_t);
@@ -177,6 +178,9 @@ int p2pvg_upsample2_bwd(const void* dy, void* dx, int dtype, int N, int H, int W
 }
 int p2pvg_gather_add(void* dst, int dtype, const float* src, const int* grp_src, int G, int64_t n, void* stream) {
   return p2pvg_gather_add_impl(dst, dtype, src, grp_src, G, n, ST);
+}
+int p2pvg_blockdiag(const void* src, int src_dtype, void* dst, int dst_dtype, int R, int C, int g, void* stream) {
+  return p2pvg_blockdiag_impl(src, src_dtype, dst, dst_dtype, R, C, g, ST);
 }
 int p2pvg_group_sum(const void* in, void* out, int dtype, const int* grp_src, int G, int F, int64_t n, void* stream) {
   return p2pvg_group_sum_impl(in, out, dtype, grp_src, G, F, n, ST);

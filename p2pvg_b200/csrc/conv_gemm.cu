@@ -193,6 +193,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;
+    __shared__ float bias_s[2 * BN];
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
       const int ph = t / (tiles_mn * splits);
@@ -228,66 +229,99 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n2 = grp_src[n / g.imgs_per_group] * g.imgs_per_group + (n % g.imgs_per_group);
         add_row = (long long)n2 * HW + (out_row - (long long)n * HW);
       }
+      // stage the bias slice of this tile in shared memory while the MMAs are still running
+      if (bias != nullptr) {
+        const int i = q * 32 + lane;
+        if (i < BN) bias_s[acc * BN + i] = (n0 + i < g.Ntot) ? bias[n0 + i] : 0.f;
+        epi_bar_sync();
+      }
+      const bool use_add = (KIND != 1) && addend != nullptr && row_ok;
+      const float* arow0 = use_add ? addend + add_row * g.Ntot + n0 : nullptr;
+      float4 a4[16];  // fp32 addend of the next 64 columns, requested before the accumulator is waited for
+      if (use_add) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(arow0 + 4 * j);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        const int nbase = n0 + c * 32;
-        if (!row_ok || nbase >= g.Ntot) continue;
-        if (KIND == 1 && partial != nullptr) {
-          float* dst = partial + ((long long)z * g.M + out_row) * g.Ntot + nbase;
+      for (int pr = 0; pr < BN / 64; pr++) {
+        // two 32-column chunks per round: both tcgen05.ld in flight before the wait; after the last round the
+        // accumulator goes back to the MMA warp *before* the global stores
+        uint32_t v2[64];
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(pr * 64);
+        tmem_ld32(taddr, v2);
+        tmem_ld32(taddr + 32, v2 + 32);
+        if (pr > 0 && use_add) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          continue;
+          for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(arow0 + pr * 64 + 4 * j);
         }
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-        if (bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) f[j] += bias[nbase + j];
+        tmem_ld_wait_dep(v2);
+        tmem_ld_wait_dep(v2 + 32);
+        if (pr == BN / 64 - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (KIND != 1 && addend) {
-          const float* ar = addend + add_row * g.Ntot + nbase;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 a4 = *reinterpret_cast<const float4*>(ar + j);
-            f[j] += a4.x; f[j + 1] += a4.y; f[j + 2] += a4.z; f[j + 3] += a4.w;
+        for (int h = 0; h < 2; h++) {
+          const int c = pr * 2 + h;
+          const uint32_t* v = v2 + 32 * h;
+          const int nbase = n0 + c * 32;
+          if (!row_ok || nbase >= g.Ntot) continue;
+          if (KIND == 1 && partial != nullptr) {
+            float* dst = partial + ((long long)z * g.M + out_row) * g.Ntot + nbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            continue;
           }
-        }
-        if (c_bf16) {
-          bf16* crow = reinterpret_cast<bf16*>(Cv) + out_row * ldc + nbase;
-          if (accumulate) {
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) f[j] += __bfloat162float(crow[j]);
+          for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+          if (bias) {
+            const float* bs = bias_s + acc * BN + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
           }
+          if (use_add) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&p0);
-            pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2);
-            pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(crow + j) = pk;
+            for (int j = 0; j < 8; j++) {
+              const float4 x4 = a4[8 * h + j];
+              f[4 * j] += x4.x; f[4 * j + 1] += x4.y; f[4 * j + 2] += x4.z; f[4 * j + 3] += x4.w;
+            }
           }
-        } else {
-          float* crow = reinterpret_cast<float*>(Cv) + out_row * ldc + nbase;
-          if (accumulate) {
+          if (c_bf16) {
+            bf16* crow = reinterpret_cast<bf16*>(Cv) + out_row * ldc + nbase;
+            if (accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) f[j] += crow[j];
+              for (int j = 0; j < 32; j++) f[j] += __bfloat162float(crow[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&p0);
+              pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2);
+              pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(crow + j) = pk;
+            }
+          } else {
+            float* crow = reinterpret_cast<float*>(Cv) + out_row * ldc + nbase;
+            if (accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) f[j] += crow[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
   tcgen05_fence_before();
@@ -412,7 +446,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   ok = ok && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
   if (kind == 1) ok = ok && (Cn % 64 == 0) && (Cm % 8 == 0);
   else ok = ok && (Ck % 64 == 0) && (Cn % 32 == 0) && (ldb % 8 == 0);
-  if (kind == 2) ok = ok && (Cn % 64 == 0);
+  if (kind == 2 || addend != nullptr) ok = ok && (Cn % 64 == 0);
   if (!ok) {
     p2pvg_set_error("conv_gemm: shape not supported by the pixel-box tiling (kind=%d N=%d H=%d W=%d Ck=%d Cn=%d)", kind, N, H, W, Ck, Cn);
     return P2PVG_ERR_UNSUPPORTED;
@@ -452,12 +486,20 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   const int BN = (g.Ntot % 128 == 0) ? 128 : 64;  // a 128-wide tile spans two filter taps when Cn == 64
   const int nkb = (int)((pix + 63) / 64);
   const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(g.Ntot, BN);
+  // split-K chosen by a small cost model (units: time of one 128x128x64 k-block on one SM, ~0.22 us): the persistent grid
+  // processes ceil(items / SMs) rounds of (k-blocks per item + fixed per-item cost); partial sums cost a write + read
   int splits = 1;
-  if (tiles < 120 && nkb >= 16) {
-    long long want = (2 * g_sms + tiles - 1) / tiles, maxs = nkb / 8;
-    splits = (int)(want < maxs ? want : maxs);
-    if (splits < 1) splits = 1;
-    while (splits > 1 && (ws == nullptr || (size_t)splits * Cm * g.Ntot * sizeof(float) > ws_bytes)) splits /= 2;
+  {
+    double best = 1e300;
+    const int maxs = nkb / 8 < 64 ? nkb / 8 : 64;
+    for (int s = 1; s <= (maxs < 1 ? 1 : maxs); s++) {
+      const int kb = cdiv(nkb, s), se = cdiv(nkb, kb);
+      if (se > 1 && (ws == nullptr || (size_t)se * Cm * g.Ntot * sizeof(float) > ws_bytes)) continue;
+      const long long rounds = cdiv((long long)tiles * se, g_sms);
+      double cost = (double)rounds * (kb + 8.0);
+      if (se > 1) cost += (double)se * Cm * g.Ntot * 8.0 / 6.0e12 / 0.22e-6;
+      if (cost < best) { best = cost; splits = se; }
+    }
   }
   int kbps = cdiv(nkb, splits);
   splits = cdiv(nkb, kbps);

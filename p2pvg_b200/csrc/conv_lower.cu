@@ -60,6 +60,48 @@ __global__ void im2col_scalar_kernel(const T* __restrict__ x, T* __restrict__ co
   }
 }
 
+// 1..4 channel images (the first encoder layer, the data gradient of the last decoder layer): one thread per
+// (output pixel, kh) copies the 4*C contiguous input elements of that filter row with vector stores
+template <typename T, int C>
+__global__ void __launch_bounds__(256) im2col_smallc_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * 4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kh = (int)(idx & 3);
+    const long long row = idx >> 2;
+    const int ox = (int)(row % Wo);
+    const long long t = row / Wo;
+    const int oy = (int)(t % Ho);
+    const long long n = t / Ho;
+    const int iy = 2 * oy - 1 + kh, ix0 = 2 * ox - 1;
+    float v[4 * C];
+    const bool yok = (iy >= 0 && iy < H);
+    const T* src = x + ((n * H + (yok ? iy : 0)) * W) * C;
+#pragma unroll
+    for (int kw = 0; kw < 4; kw++) {
+      const int ix = ix0 + kw;
+      const bool ok = yok && ix >= 0 && ix < W;
+#pragma unroll
+      for (int c = 0; c < C; c++) v[kw * C + c] = ok ? ld_f<T>(src + (long long)ix * C + c) : 0.f;
+    }
+    T* dst = col + idx * (4 * C);
+    if (sizeof(T) == 2) {
+#pragma unroll
+      for (int j = 0; j < C; j++) {  // 4 bf16 = 8 bytes per store
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[4 * j], v[4 * j + 1]), p1 = __floats2bfloat162_rn(v[4 * j + 2], v[4 * j + 3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(dst) + 4 * j) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; j++)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+}
+
 // ---- col2im (gather form): y [N,2Hi,2Wi,C] <- col [N*Hi*Wi, 16*C] (+ col2 of a shared source) ----
 template <typename T, int V>
 __global__ void __launch_bounds__(256) col2im_k4s2p1_kernel(const T* __restrict__ col, const T* __restrict__ col2,
@@ -185,6 +227,22 @@ __global__ void group_sum_kernel(const T* __restrict__ in, T* __restrict__ out, 
   }
 }
 
+// dst[(gi,r), (gj,c)] = (gi == gj) ? src[r, c] : 0   -- g copies of a small weight matrix on the diagonal, so that g
+// consecutive rows of a thin [M, C] operand can be multiplied as one [M/g, g*C] row without out-of-bounds TMA boxes
+template <typename TS, typename TD>
+__global__ void blockdiag_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int C, int g) {
+  const long long total = (long long)g * R * g * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long t = idx / C;
+    const int gj = (int)(t % g);
+    t /= g;
+    const int r = (int)(t % R);
+    const int gi = (int)(t / R);
+    st_f<TD>(dst + idx, gi == gj ? ld_f<TS>(src + (long long)r * C + c) : 0.f);
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 64;
@@ -201,6 +259,14 @@ int p2pvg_im2col_k4s2p1_impl(const void* x, void* col, int dtype, int N, int H, 
   if (C % vec == 0 && aligned) {
     long long total = (long long)N * (H / 2) * (W / 2) * 16 * (C / vec);
     DISPATCH_DTYPE(dtype, T, (im2col_vec_kernel<T><<<grid_for((total + 3) / 4, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
+  } else if (C <= 4 && (reinterpret_cast<uintptr_t>(col) & 15) == 0) {
+    long long total = (long long)N * (H / 2) * (W / 2) * 4;
+#define P2PVG_SMALLC(CC) DISPATCH_DTYPE(dtype, T, (im2col_smallc_kernel<T, CC><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W)))
+    if (C == 1) P2PVG_SMALLC(1);
+    else if (C == 2) P2PVG_SMALLC(2);
+    else if (C == 3) P2PVG_SMALLC(3);
+    else P2PVG_SMALLC(4);
+#undef P2PVG_SMALLC
   } else {
     long long total = (long long)N * (H / 2) * (W / 2) * 16 * C;
     DISPATCH_DTYPE(dtype, T, (im2col_scalar_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C)));
@@ -258,6 +324,20 @@ int p2pvg_add_indexed_impl(void* dst, const void* src, int dtype, const int* dst
   if (F == 0 || n == 0) return P2PVG_OK;
   DISPATCH_DTYPE(dtype, T, (add_indexed_kernel<T><<<grid_for((long long)F * n, 256), 256, 0, st>>>((T*)dst, (const T*)src, dst_idx, F, n)));
   return p2pvg_check_launch("add_indexed");
+}
+
+int p2pvg_blockdiag_impl(const void* src, int src_dtype, void* dst, int dst_dtype, int R, int C, int g, cudaStream_t st) {
+  P2PVG_REQUIRE(R > 0 && C > 0 && g > 0, P2PVG_ERR_BAD_ARG, "blockdiag: bad shape");
+  const long long total = (long long)g * R * g * C;
+  const int grid = grid_for(total, 256);
+  if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_F32) blockdiag_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, R, C, g);
+  else if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_BF16) blockdiag_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, R, C, g);
+  else if (src_dtype == P2PVG_BF16 && dst_dtype == P2PVG_BF16) blockdiag_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, R, C, g);
+  else {
+    p2pvg_set_error("blockdiag: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+    return P2PVG_ERR_BAD_ARG;
+  }
+  return p2pvg_check_launch("blockdiag");
 }
 
 int p2pvg_group_sum_impl(const void* in, void* out, int dtype, const int* grp_src, int G, int F, long long n, cudaStream_t st) {

@@ -96,8 +96,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// tcgen05.wait::ld that also names the destination registers of a preceding tcgen05.ld as in/out operands, so that the
+// compiler cannot schedule a read of them above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+// named barrier among the four epilogue warps (barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version bit set)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -236,6 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const bool split = (partial != nullptr);
+    __shared__ float bias_s[2 * BN];
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
       const int z = t / tiles_mn, r = t - z * tiles_mn;
@@ -243,94 +256,115 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
       const long long m = (long long)m0 + q * 32 + lane;
       const bool row_ok = m < M;
+      // stage the bias slice of this tile in shared memory while the MMAs are still running
+      if (bias != nullptr && !split) {
+        const int i = q * 32 + lane;
+        if (i < BN) bias_s[acc * BN + i] = (n0 + i < N) ? bias[n0 + i] : 0.f;
+        epi_bar_sync();
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        const int nbase = n0 + c * 32;
-        if (!row_ok || nbase >= N) continue;
-        if (split) {
-          float* dst = partial + ((long long)z * M + m) * N + nbase;
-          if (nbase + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (nbase + j < N) dst[j] = __uint_as_float(v[j]);
-          }
-          continue;
+      for (int pr = 0; pr < BN / 64; pr++) {
+        // two 32-column chunks per round: both tcgen05.ld in flight before one wait; after the last round the
+        // accumulator is handed back to the MMA warp *before* the global stores
+        uint32_t v2[64];
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(pr * 64);
+        tmem_ld32(taddr, v2);
+        tmem_ld32(taddr + 32, v2 + 32);
+        tmem_ld_wait_dep(v2);
+        tmem_ld_wait_dep(v2 + 32);
+        if (pr == BN / 64 - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-        if (bias) {
+        for (int h = 0; h < 2; h++) {
+          const int c = pr * 2 + h;
+          const uint32_t* v = v2 + 32 * h;
+          const int nbase = n0 + c * 32;
+          if (!row_ok || nbase >= N) continue;
+          if (split) {
+            float* dst = partial + ((long long)z * M + m) * N + nbase;
+            if (nbase + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (nbase + j < N) f[j] += bias[nbase + j];
-        }
-        if (c_bf16) {
-          bf16* crow = reinterpret_cast<bf16*>(Cv) + m * ldc + nbase;
-          if (addend) {
-            const bf16* arow = reinterpret_cast<const bf16*>(addend) + m * ldd + nbase;
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (nbase + j < N) f[j] += __bfloat162float(arow[j]);
+              for (int j = 0; j < 32; j++)
+                if (nbase + j < N) dst[j] = __uint_as_float(v[j]);
+            }
+            continue;
           }
-          if (accumulate) {
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (nbase + j < N) f[j] += __bfloat162float(crow[j]);
+          for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+          if (bias) {
+            const float* bs = bias_s + acc * BN + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
           }
-          const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-          if (vec) {
+          if (c_bf16) {
+            bf16* crow = reinterpret_cast<bf16*>(Cv) + m * ldc + nbase;
+            if (addend) {
+              const bf16* arow = reinterpret_cast<const bf16*>(addend) + m * ldd + nbase;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&p0);
-              pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2);
-              pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(crow + j) = pk;
+              for (int j = 0; j < 32; j++)
+                if (nbase + j < N) f[j] += __bfloat162float(arow[j]);
+            }
+            if (accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (nbase + j < N) f[j] += __bfloat162float(crow[j]);
+            }
+            const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0);
+                pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2);
+                pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(crow + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (nbase + j < N) crow[j] = __float2bfloat16_rn(f[j]);
             }
           } else {
+            float* crow = reinterpret_cast<float*>(Cv) + m * ldc + nbase;
+            if (addend) {
+              const float* arow = reinterpret_cast<const float*>(addend) + m * ldd + nbase;
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (nbase + j < N) crow[j] = __float2bfloat16_rn(f[j]);
-          }
-        } else {
-          float* crow = reinterpret_cast<float*>(Cv) + m * ldc + nbase;
-          if (addend) {
-            const float* arow = reinterpret_cast<const float*>(addend) + m * ldd + nbase;
+              for (int j = 0; j < 32; j++)
+                if (nbase + j < N) f[j] += arow[j];
+            }
+            if (accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (nbase + j < N) f[j] += arow[j];
-          }
-          if (accumulate) {
+              for (int j = 0; j < 32; j++)
+                if (nbase + j < N) f[j] += crow[j];
+            }
+            const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+            if (vec) {
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (nbase + j < N) f[j] += crow[j];
-          }
-          const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-          if (vec) {
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (nbase + j < N) crow[j] = f[j];
+              for (int j = 0; j < 32; j++)
+                if (nbase + j < N) crow[j] = f[j];
+            }
           }
         }
       }
-      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): hand the accumulator back
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
   tcgen05_fence_before();

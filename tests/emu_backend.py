@@ -109,6 +109,10 @@ class EmuKernels:
         idx = dst_idx[:F_].long()
         d[idx] = (d[idx].float() + s).to(dst.dtype)
 
+    def blockdiag(self, src, dst, R, C, g):
+        m = _flat(src, R * C).reshape(R, C).float()
+        _flat(dst, g * R * g * C).copy_(torch.block_diag(*([m] * g)).reshape(-1).to(dst.dtype))
+
     def group_sum(self, inp, out, grp_src, G, F_, n):
         i = _flat(inp, G * n).reshape(G, n).float()
         o = torch.zeros(F_, n, device=inp.device)

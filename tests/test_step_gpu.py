@@ -134,7 +134,8 @@ def digest_close(t, d, rtol, what):
     assert abs(float(f.norm()) - d["l2"]) <= rtol * max(d["l2"], 1e-30), what
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "step_*.pt"))), ids=lambda p: os.path.basename(p)[5:-3])
+# the dcgan fixtures; vgg64_rgb and h36m_mlp are replayed by tests/test_vgg_gpu.py / tests/test_mlp_gpu.py
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "step_d*.pt"))), ids=lambda p: os.path.basename(p)[5:-3])
 def test_step_vs_reference_golden(path):
     """fp32 CUDA path against numbers produced by the reference's own P2PModel.forward."""
     fix = torch.load(path, weights_only=False)
