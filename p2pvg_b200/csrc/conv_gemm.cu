@@ -15,6 +15,7 @@
 // kind 3  y[N,H,W,Cn] = conv3x3_s1_p1(x[N,H,W,Ck]) . W[Cn, (tap, Ck)] + bias + addend      vgg layer forward (kind 0 geometry, 9 taps)
 // kind 4  g[Cm, (tap, Cn)] = sum_pix a[pix, Cm]^T . gather_3x3(b)[pix, tap, Cn]             vgg weight gradients (kind 1 geometry)
 // kind 5  kind 3 with mirrored tap offsets (pixel - (kh-1, kw-1)): the data gradient of a 3x3 convolution
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -30,7 +31,8 @@ constexpr int A_STAGE_BYTES = BLOCK_M * 128;
 template <int BN> struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 128) ? 6 : 8;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;  // 128x256 tiles: 87 FLOP per smem-fill byte (L2 -> SM
+                                                                        // bandwidth bounds the 128x128 tiles at ~1100 TFLOP/s)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
 };
 
@@ -231,8 +233,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // stage the bias slice of this tile in shared memory while the MMAs are still running
       if (bias != nullptr) {
-        const int i = q * 32 + lane;
-        if (i < BN) bias_s[acc * BN + i] = (n0 + i < g.Ntot) ? bias[n0 + i] : 0.f;
+        for (int i = q * 32 + lane; i < BN; i += 128) bias_s[acc * BN + i] = (n0 + i < g.Ntot) ? bias[n0 + i] : 0.f;
         epi_bar_sync();
       }
       const bool use_add = (KIND != 1) && addend != nullptr && row_ok;
@@ -350,7 +351,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_enc = nullptr;
 std::once_flag g_once2;
 int g_sms = 148;
-int g_attr[3][2] = {};
+int g_bn256 = 1;  // P2PVG_CONV_BN256=0 keeps the 128-wide tiles (A/B comparison)
+int g_attr[3][3] = {};
 
 void resolve2() {
   int dev = 0, sms = 0;
@@ -360,6 +362,8 @@ void resolve2() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
     g_enc = reinterpret_cast<EncodeTiledFn>(fn);
   (void)cudaGetLastError();
+  const char* e = getenv("P2PVG_CONV_BN256");
+  if (e != nullptr && e[0] == '0') g_bn256 = 0;
 }
 
 int map2d(CUtensorMap* m, const void* base, long long dim0, long long dim1, long long ld, int box1) {
@@ -409,7 +413,7 @@ template <int KIND, int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, const Geom& g, int accumulate,
            const float* bias, const float* addend, const int* grp_src, float* partial, int splits, int kb_per_split, cudaStream_t st) {
   auto kern = conv_gemm_kernel<KIND, BN>;
-  int& done = g_attr[KIND][BN == 128];
+  int& done = g_attr[KIND][BN == 256 ? 2 : BN == 128];
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -458,10 +462,11 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
     g.M = (int)pix; g.Ntot = Cn;
     rc = map4d(&ta, a, N, g.st * H, g.st * W, Ck, W, g.bh128, g.bn128, g.st);
     if (rc) return rc;
-    const int BN = Cn > 64 ? 128 : 64;
+    const int BN = (Cn % 256 == 0 && g_bn256) ? 256 : Cn > 64 ? 128 : 64;
     rc = map2d(&tb, b, (long long)taps * Ck, Cn, ldb, BN);
     if (rc) return rc;
     const int nkb = taps * (Ck / 64);
+    if (BN == 256) return launch<0, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
     if (BN == 128) return launch<0, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
     return launch<0, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
   }
@@ -472,7 +477,8 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
     rc = map2d(&tb, b, 16LL * Cn, Ck, ldb, 64);  // MN-major weight [Ck rows][16*Cn]
     if (rc) return rc;
     const int nkb = 4 * (Ck / 64);
-    const int BN = Cn > 64 ? 128 : 64;
+    const int BN = (Cn % 256 == 0 && g_bn256) ? 256 : Cn > 64 ? 128 : 64;
+    if (BN == 256) return launch<2, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
     if (BN == 128) return launch<2, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
     return launch<2, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
   }
@@ -483,7 +489,9 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   if (rc) return rc;
   rc = map4d(&tb, b, N, g.st * H, g.st * W, Cn, W, g.bh64, g.bn64, g.st);
   if (rc) return rc;
-  const int BN = (g.Ntot % 128 == 0) ? 128 : 64;  // a 128-wide tile spans two filter taps when Cn == 64
+  // a wide tile spans several filter taps when Cn == 64; 256-wide tiles pay off while there are few output tiles (measured)
+  const bool wide = g.Ntot % 256 == 0 && g_bn256 && (long long)cdiv(Cm, BLOCK_M) * (g.Ntot / 128) <= 64;
+  const int BN = wide ? 256 : (g.Ntot % 128 == 0) ? 128 : 64;
   const int nkb = (int)((pix + 63) / 64);
   const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(g.Ntot, BN);
   // split-K chosen by a small cost model (units: time of one 128x128x64 k-block on one SM, ~0.22 us): the persistent grid
@@ -497,14 +505,15 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
       if (se > 1 && (ws == nullptr || (size_t)se * Cm * g.Ntot * sizeof(float) > ws_bytes)) continue;
       const long long rounds = cdiv((long long)tiles * se, g_sms);
       double cost = (double)rounds * (kb + 8.0);
-      if (se > 1) cost += (double)se * Cm * g.Ntot * 8.0 / 6.0e12 / 0.22e-6;
+      if (se > 1) cost += (double)se * Cm * g.Ntot * 8.0 / 6.0e12 / (0.22e-6 * BN / 128);
       if (cost < best) { best = cost; splits = se; }
     }
   }
   int kbps = cdiv(nkb, splits);
   splits = cdiv(nkb, kbps);
   float* partial = splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
-  if (BN == 128) rc = launch<1, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
+  if (BN == 256) rc = launch<1, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
+  else if (BN == 128) rc = launch<1, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
   else rc = launch<1, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
   if (rc) return rc;
   if (splits > 1) {

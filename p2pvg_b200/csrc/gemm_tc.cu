@@ -258,8 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = m < M;
       // stage the bias slice of this tile in shared memory while the MMAs are still running
       if (bias != nullptr && !split) {
-        const int i = q * 32 + lane;
-        if (i < BN) bias_s[acc * BN + i] = (n0 + i < N) ? bias[n0 + i] : 0.f;
+        for (int i = q * 32 + lane; i < BN; i += 128) bias_s[acc * BN + i] = (n0 + i < N) ? bias[n0 + i] : 0.f;
         epi_bar_sync();
       }
       mbar_wait(&tmem_full_bar[acc], acc_ph);

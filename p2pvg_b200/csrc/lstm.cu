@@ -263,6 +263,16 @@ int p2pvg_align_impl(const float* H, const int* in_idx, const float* h_pred, int
 int p2pvg_colsum_impl(const void* x, int dtype, long long rows, int cols, long long ld, float* out, int accumulate, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   if (cols == 0) return P2PVG_OK;
+  // very thin contiguous matrices (bias gradient of a 1/3-channel layer): fold 256 rows into one so that a warp reads 32
+  // consecutive elements, then sum the 256*cols folded columns per original column
+  constexpr int FOLD = 256;
+  if (cols <= 4 && ld == cols && rows >= 64 * FOLD && rows % FOLD == 0 && ws != nullptr &&
+      ws_bytes >= (size_t)(1025 * FOLD * cols) * sizeof(float)) {
+    float* tmp = reinterpret_cast<float*>(ws) + (size_t)1024 * FOLD * cols;
+    int rc = p2pvg_colsum_impl(x, dtype, rows / FOLD, FOLD * cols, (long long)FOLD * cols, tmp, 0, ws, (size_t)1024 * FOLD * cols * sizeof(float), st);
+    if (rc) return rc;
+    return p2pvg_colsum_impl(tmp, P2PVG_F32, FOLD, cols, cols, out, accumulate, ws, (size_t)1024 * FOLD * cols * sizeof(float), st);
+  }
   // enough chunks to fill the machine (148 SMs x a few blocks), at least 64 rows per chunk
   long long want = (148LL * 8) / cdiv(cols, 32) + 1;
   long long maxc = (rows + 63) / 64;

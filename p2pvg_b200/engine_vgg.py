@@ -145,8 +145,11 @@ class TrainEngineVGG(TrainEngine):
         N = T * B
         hw = 64 * 64
         xs = x.contiguous()
-        self.x_nhwc = self.fbuf("x_nhwc", N * hw * nc)
-        K.permute4(xs, self.x_nhwc, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
+        if nc == 1 and xs.dtype == torch.float32:
+            self.x_nhwc = xs.view(-1)  # one channel: NCHW == NHWC, the MSE target is the input itself
+        else:
+            self.x_nhwc = self.fbuf("x_nhwc", N * hw * nc)
+            K.permute4(xs, self.x_nhwc, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
         if self.adt == torch.float32:
             a = self.x_nhwc
         else:
