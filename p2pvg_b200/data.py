@@ -1,0 +1,81 @@
+"""Host -> device input pipeline for the train step ("device-side data path").
+
+The reference loop (train.py:212, data/data_utils.py:129-137) does ``x = next(generator); x = x.cuda()`` and then calls the
+model, so the H2D copy of a 126 MB batch (T=30, B=256, 64x64) sits on the critical path of every step.
+``DevicePrefetcher`` wraps any iterator of host batches: batch i+1 is copied from pinned memory on a side stream while
+batch i trains, and is handed out only after the compute stream has been made to wait for its copy.
+
+    for x in DevicePrefetcher(loader, device):      # x: device tensor, time-major like the reference's normalize_data
+        losses = model(x, 0, cp_ix)
+"""
+from __future__ import annotations
+
+import torch
+
+
+class DevicePrefetcher:
+    def __init__(self, batches, device, depth: int = 2):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DevicePrefetcher copies to a CUDA device")
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.depth = max(2, int(depth))
+        self.slots = [None] * self.depth      # device buffers, reused round-robin
+        self.free_ev = [None] * self.depth    # compute-stream event: the slot's previous consumer has been enqueued
+        self.pinned = [None] * self.depth
+        self.n = 0
+        self.queue = []
+        self._fill()
+
+    def _issue(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            return False
+        k = self.n % self.depth
+        self.n += 1
+        if not host.is_pinned():  # page-locked staging buffer (reused); pinned inputs are copied from directly
+            if self.pinned[k] is None or self.pinned[k].shape != host.shape or self.pinned[k].dtype != host.dtype:
+                self.pinned[k] = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
+            self.pinned[k].copy_(host)
+            host = self.pinned[k]
+        if self.slots[k] is None or self.slots[k].shape != host.shape or self.slots[k].dtype != host.dtype:
+            self.slots[k] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.free_ev[k] is not None:
+                self.copy_stream.wait_event(self.free_ev[k])   # do not overwrite a batch the step may still read
+            self.slots[k].copy_(host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        self.queue.append((k, ready))
+        return True
+
+    def _fill(self):
+        while len(self.queue) < self.depth - 1 and self._issue():
+            pass
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if not self.queue:
+            self._fill()
+            if not self.queue:
+                raise StopIteration
+        k, ready = self.queue.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ready)
+        x = self.slots[k]
+        ev = torch.cuda.Event()
+        self.free_ev[k] = ev
+        self._fill()          # start copying the next batch before the caller blocks on this step's results
+        # the caller enqueues its work after this returns; `release` marks the point after which slot k may be refilled
+        self._pending_release = (k, ev)
+        return x
+
+    def release(self):
+        """Record that everything enqueued so far has consumed the last batch (call after the step; optional when the
+        consumer copies the batch into its own static buffer first, as the CUDA-graph step does)."""
+        k, ev = self._pending_release
+        ev.record(torch.cuda.current_stream(self.device))
