@@ -316,9 +316,22 @@ def main():
                     roofline=roof, cpu_baseline=cpu,
                     e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=int(x_host.numel() * 4), d2h_bytes_per_step=16),
                     gpu_launches=int(launches), clocks=clocks, losses=[float(v) for v in losses])
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tear-down must never hang the launcher: drop the CUDA graphs that hold captured NCCL kernels, give
+        # destroy_process_group a bounded time, then leave without running interpreter-exit hooks
+        import gc
+        import threading
+        barrier()
+        torch.cuda.synchronize()
+        eng._graphs.clear()
+        gc.collect()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(15)
+        os._exit(0)
 
 
 if __name__ == "__main__":
