@@ -118,6 +118,9 @@ int p2pvg_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, con
                    const int64_t* src_strides /*host*/, int accumulate, void* stream);
 int p2pvg_add_indexed(void* dst, const void* src, int dtype, const int* dst_idx, int F, int64_t n, void* stream);
 int p2pvg_group_sum(const void* in, void* out, int dtype, const int* grp_src, int G, int F, int64_t n, void* stream);
+/* dst[a][q][p] = src[a][p][q] for a < A (tiled, coalesced both ways): nn.Conv2d / nn.ConvTranspose2d weights
+ * [A][B][kh*kw] -> the GEMM layout [A][(kh,kw)][B] (models/dcgan_64.py:8,20) and the weight gradients back. */
+int p2pvg_transpose_batched(const void* src, int src_dtype, void* dst, int dst_dtype, int A, int P, int Q, void* stream);
 /* dst[g*R, g*C] = blockdiag(src[R, C], ..., src[R, C]): lets the 1/3-channel ends of the conv stacks (K = 16*nc or N = 16*nc,
  * models/dcgan_64.py:34,76) run as [M/g, g*C] GEMMs whose TMA boxes are never out of bounds. */
 int p2pvg_blockdiag(const void* src, int src_dtype, void* dst, int dst_dtype, int R, int C, int g, void* stream);

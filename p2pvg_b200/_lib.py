@@ -176,6 +176,10 @@ class CudaKernels:
     def add_indexed(self, dst, src, dst_idx, F, n):
         self._ck(self.lib.p2pvg_add_indexed(_p(dst), _p(src), _i(_dt(dst)), _p(dst_idx), _i(F), _i64(n), self._stream()))
 
+    def transpose_batched(self, src, dst, A, P, Q):
+        """dst[a][q][p] = src[a][p][q]"""
+        self._ck(self.lib.p2pvg_transpose_batched(_p(src), _i(_dt(src)), _p(dst), _i(_dt(dst)), _i(A), _i(P), _i(Q), self._stream()))
+
     def blockdiag(self, src, dst, R, C, g):
         self._ck(self.lib.p2pvg_blockdiag(_p(src), _i(_dt(src)), _p(dst), _i(_dt(dst)), _i(R), _i(C), _i(g), self._stream()))
 

@@ -57,6 +57,7 @@ int p2pvg_permute4_impl(const void*, int, void*, int, const int*, const long lon
 int p2pvg_add_indexed_impl(void*, const void*, int, const int*, int, long long, cudaStream_t);
 int p2pvg_group_sum_impl(const void*, void*, int, const int*, int, int, long long, cudaStream_t);
 int p2pvg_blockdiag_impl(const void*, int, void*, int, int, int, int, cudaStream_t);
+int p2pvg_transpose_batched_impl(const void*, int, void*, int, int, int, int, cudaStream_t);
 size_t p2pvg_bn_workspace_bytes_impl(int, int);
 int p2pvg_bn_fwd_stats_impl(const void*, int, int, long long, int, const float*, const float*, float, void*, size_t, float*, float*,
                             float*, float*, float*, cudaStream_t);
@@ -183,6 +184,9 @@ int p2pvg_upsample2_bwd(const void* dy, void* dx, int dtype, int N, int H, int W
 }
 int p2pvg_gather_add(void* dst, int dtype, const float* src, const int* grp_src, int G, int64_t n, void* stream) {
   return p2pvg_gather_add_impl(dst, dtype, src, grp_src, G, n, ST);
+}
+int p2pvg_transpose_batched(const void* src, int src_dtype, void* dst, int dst_dtype, int A, int P, int Q, void* stream) {
+  return p2pvg_transpose_batched_impl(src, src_dtype, dst, dst_dtype, A, P, Q, ST);
 }
 int p2pvg_blockdiag(const void* src, int src_dtype, void* dst, int dst_dtype, int R, int C, int g, void* stream) {
   return p2pvg_blockdiag_impl(src, src_dtype, dst, dst_dtype, R, C, g, ST);

@@ -243,6 +243,30 @@ __global__ void blockdiag_kernel(const TS* __restrict__ src, TD* __restrict__ ds
   }
 }
 
+// batched 2-D transpose  dst[a][q][p] = src[a][p][q]  through a 32x33 shared-memory tile: both the reads and the writes
+// are coalesced.  Packs conv weights W[Cout][Cin][taps] -> [Cout][taps][Cin] (and back for the weight gradients), where
+// the generic strided gather of permute4 touches one 4-byte element per 64-byte segment.
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int P, int Q) {
+  __shared__ float tile[32][33];
+  const long long a = blockIdx.z;
+  const int p0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
+  const TS* s = src + a * P * Q;
+  TD* d = dst + a * P * Q;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int p = p0 + ty + i, q = q0 + tx;
+    if (p < P && q < Q) tile[ty + i][tx] = ld_f<TS>(s + (long long)p * Q + q);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int q = q0 + ty + i, pp = p0 + tx;
+    if (q < Q && pp < P) st_f<TD>(d + (long long)q * P + pp, tile[tx][ty + i]);
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 64;
@@ -324,6 +348,19 @@ int p2pvg_add_indexed_impl(void* dst, const void* src, int dtype, const int* dst
   if (F == 0 || n == 0) return P2PVG_OK;
   DISPATCH_DTYPE(dtype, T, (add_indexed_kernel<T><<<grid_for((long long)F * n, 256), 256, 0, st>>>((T*)dst, (const T*)src, dst_idx, F, n)));
   return p2pvg_check_launch("add_indexed");
+}
+
+int p2pvg_transpose_batched_impl(const void* src, int src_dtype, void* dst, int dst_dtype, int A, int P, int Q, cudaStream_t st) {
+  P2PVG_REQUIRE(A > 0 && P > 0 && Q > 0 && A <= 65535, P2PVG_ERR_BAD_ARG, "transpose_batched: bad shape %d x %d x %d", A, P, Q);
+  dim3 grid(cdiv(Q, 32), cdiv(P, 32), A);
+  if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_F32) transpose_batched_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, P, Q);
+  else if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_BF16) transpose_batched_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, P, Q);
+  else if (src_dtype == P2PVG_BF16 && dst_dtype == P2PVG_BF16) transpose_batched_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, P, Q);
+  else {
+    p2pvg_set_error("transpose_batched: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+    return P2PVG_ERR_BAD_ARG;
+  }
+  return p2pvg_check_launch("transpose_batched");
 }
 
 int p2pvg_blockdiag_impl(const void* src, int src_dtype, void* dst, int dst_dtype, int R, int C, int g, cudaStream_t st) {

@@ -201,7 +201,7 @@ class TrainEngine:
                 w = P[self.enc_names(l)[0] + ".weight"]
                 co, ci = w.shape[0], w.shape[1]
                 wp = self.buf(f"wp_enc{l}", co * 16 * ci)
-                K.permute4(w, wp, (co, 4, 4, ci), (ci * 16, 4, 1, 16))
+                K.transpose_batched(w, wp, co, ci, 16)   # [co][ci][tap] -> [co][tap][ci]
                 self._packed[f"enc{l}"] = wp
                 if self.bd and l == 0 and (16 * ci) % 64 != 0:
                     bd = self.buf("wbd_enc0", 4 * co * 64 * ci)
@@ -216,7 +216,7 @@ class TrainEngine:
                 w = P[cn + ".weight"]
                 ci, co = w.shape[0], w.shape[1]
                 wp = self.buf(f"wp_dec{k}", ci * 16 * co)
-                K.permute4(w, wp, (ci, 4, 4, co), (co * 16, 4, 1, 16))
+                K.transpose_batched(w, wp, ci, co, 16)   # [ci][co][tap] -> [ci][tap][co]
                 self._packed[f"dec{k}"] = wp
                 if self.bd and k == self.n - 1 and (16 * co) % 64 != 0:
                     cd = ci // 2
@@ -251,7 +251,7 @@ class TrainEngine:
                     ([("output.0.weight", (self.g, R))] if m == "frame_predictor" else []):
                 o, i = shape
                 wt = self.fbuf(f"{m}_{name}_T", o * i)
-                K.permute4(P[name], wt, (i, o, 1, 1), (1, i, 0, 0))
+                K.transpose_batched(P[name], wt, 1, o, i)   # [o][i] -> [i][o]
                 self._packed[f"{m}.{name}.T"] = wt
 
     def lin_dinput(self, m, name, dY, out, rows, out_dim, in_dim, **kw):
@@ -711,7 +711,7 @@ class TrainEngine:
                     if want_wgrad:
                         K.gemm(rec["skip"], dcolS, gw[cd * 16 * cout:], cd, 16 * cout, Ms, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
             if want_wgrad:
-                K.permute4(gw, A.g[cn + ".weight"], (2 * cd, cout, 4, 4), (16 * cout, 1, 4 * cout, cout))
+                K.transpose_batched(gw, A.g[cn + ".weight"], 2 * cd, 16, cout)   # [2cd][tap][co] -> [2cd][co][tap]
             dy = dd
         # upc1: BatchNorm + LeakyReLU, then the g -> 4x4xCtop GEMM
         ctop = self.chans[-1]
@@ -726,7 +726,7 @@ class TrainEngine:
             A.g[cn + ".bias"].zero_()
             gw = self.fbuf("gwp_dec-1", g * 16 * ctop)
             K.gemm(hp, dy, gw, g, 16 * ctop, N, a_mn=True, b_mn=True, lda=g, ldb=16 * ctop)
-            K.permute4(gw, A.g[cn + ".weight"], (g, ctop, 4, 4), (16 * ctop, 1, 4 * ctop, ctop))
+            K.transpose_batched(gw, A.g[cn + ".weight"], g, 16, ctop)
         dhp = self.d_hpred[g0 * B * g:g1 * B * g]
         if self.adt == torch.float32:
             K.gemm(dy, self._packed["dec-1"], dhp, N, g, 16 * ctop)
@@ -882,7 +882,7 @@ class TrainEngine:
         ctop = self.chans[-1]
         gw = self.fbuf(f"gwp_enc{n}", g * 16 * ctop)
         K.gemm(dy, fin["inp"], gw, g, 16 * ctop, N, a_mn=True, b_mn=True, lda=g, ldb=16 * ctop)
-        K.permute4(gw, A.g[cn + ".weight"], (g, ctop, 4, 4), (16 * ctop, 1, 4 * ctop, ctop))
+        K.transpose_batched(gw, A.g[cn + ".weight"], g, 16, ctop)
         gy = self.buf(f"enc_gy{n - 1}", N * 16 * ctop)
         K.gemm(dy, self._packed[f"enc{n}"], gy, N, 16 * ctop, g, b_mn=True)
         for l in range(n - 1, -1, -1):
@@ -907,7 +907,7 @@ class TrainEngine:
                     col = self.buf(f"enc_col{l}", M * 16 * cin)
                     K.im2col(rec["inp"], col, N, rec["Hin"], rec["Hin"], cin)
                 K.gemm(gy, col, gw, cout, 16 * cin, M, a_mn=True, b_mn=True, lda=cout, ldb=16 * cin)
-            K.permute4(gw, A.g[cn + ".weight"], (cout, cin, 4, 4), (16 * cin, 1, 4 * cin, cin))
+            K.transpose_batched(gw, A.g[cn + ".weight"], cout, 16, cin)   # [co][tap][ci] -> [co][ci][tap]
             if l > 0:
                 gprev = self.buf(f"enc_gy{l - 1}", N * rec["Hin"] * rec["Hin"] * cin)
                 if rec["imp"]:

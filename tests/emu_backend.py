@@ -109,6 +109,10 @@ class EmuKernels:
         idx = dst_idx[:F_].long()
         d[idx] = (d[idx].float() + s).to(dst.dtype)
 
+    def transpose_batched(self, src, dst, A, P, Q):
+        m = _flat(src, A * P * Q).reshape(A, P, Q).float()
+        _flat(dst, A * P * Q).copy_(m.transpose(1, 2).reshape(-1).to(dst.dtype))
+
     def blockdiag(self, src, dst, R, C, g):
         m = _flat(src, R * C).reshape(R, C).float()
         _flat(dst, g * R * g * C).copy_(torch.block_diag(*([m] * g)).reshape(-1).to(dst.dtype))
