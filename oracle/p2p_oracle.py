@@ -118,6 +118,18 @@ def _dcgan_decoder_container(g_dim, nc, width):
 
 VGG_ENC = [[(None, 64), (64, 64)], [(64, 128), (128, 128)], [(128, 256), (256, 256), (256, 256)], [(256, 512), (512, 512), (512, 512)]]
 VGG_DEC = [[(1024, 512), (512, 512), (512, 256)], [(512, 256), (256, 256), (256, 128)], [(256, 128), (128, 64)], [(128, 64)]]
+# models/vgg_128.py:16-105: one more 512-channel stage on both sides
+VGG_ENC_128 = VGG_ENC + [[(512, 512), (512, 512), (512, 512)]]
+VGG_DEC_128 = [[(1024, 512), (512, 512), (512, 512)]] + VGG_DEC
+
+
+def _vgg_lists(width):
+    return (VGG_ENC_128, VGG_DEC_128) if width == 128 else (VGG_ENC, VGG_DEC)
+
+
+def _vgg_width(p):
+    """64 or 128, from the state_dict keys (vgg_128 has a c6 / upc6)."""
+    return 128 if any(k.startswith(("c6.", "upc6.")) for k in p) else 64
 
 
 def _vgg_layer(nin, nout):
@@ -127,24 +139,26 @@ def _vgg_layer(nin, nout):
     return blk
 
 
-def _vgg_encoder_container(g_dim, nc):
-    """models/vgg_64.py:16-48."""
+def _vgg_encoder_container(g_dim, nc, width=64):
+    """models/vgg_64.py:16-48, models/vgg_128.py:16-54."""
     nn = torch.nn
     m = nn.Module()
-    for i, stage in enumerate(VGG_ENC, 1):
+    enc = _vgg_lists(width)[0]
+    for i, stage in enumerate(enc, 1):
         setattr(m, f"c{i}", nn.Sequential(*[_vgg_layer(nc if a is None else a, b) for a, b in stage]))
-    m.c5 = nn.Sequential(nn.Conv2d(512, g_dim, 4, 1, 0), nn.BatchNorm2d(g_dim), nn.Tanh())
+    setattr(m, f"c{len(enc) + 1}", nn.Sequential(nn.Conv2d(512, g_dim, 4, 1, 0), nn.BatchNorm2d(g_dim), nn.Tanh()))
     return m
 
 
-def _vgg_decoder_container(g_dim, nc):
-    """models/vgg_64.py:59-92."""
+def _vgg_decoder_container(g_dim, nc, width=64):
+    """models/vgg_64.py:59-92, models/vgg_128.py:66-105."""
     nn = torch.nn
     m = nn.Module()
+    dec = _vgg_lists(width)[1]
     m.upc1 = nn.Sequential(nn.ConvTranspose2d(g_dim, 512, 4, 1, 0), nn.BatchNorm2d(512), nn.LeakyReLU(LRELU))
-    for i, stage in enumerate(VGG_DEC[:3], 2):
+    for i, stage in enumerate(dec[:-1], 2):
         setattr(m, f"upc{i}", nn.Sequential(*[_vgg_layer(a, b) for a, b in stage]))
-    m.upc5 = nn.Sequential(_vgg_layer(128, 64), nn.ConvTranspose2d(64, nc, 3, 1, 1), nn.Sigmoid())
+    setattr(m, f"upc{len(dec) + 1}", nn.Sequential(_vgg_layer(128, 64), nn.ConvTranspose2d(64, nc, 3, 1, 1), nn.Sigmoid()))
     return m
 
 
@@ -154,30 +168,35 @@ def _vgg_block(p, pre, x, training=True):
 
 
 def vgg_encoder_fwd(p, x, training=True):
-    """models/vgg_64.py:50-56."""
+    """models/vgg_64.py:50-56, models/vgg_128.py:56-63."""
     skips, h = [], x
-    for i, stage in enumerate(VGG_ENC, 1):
+    enc = _vgg_lists(_vgg_width(p))[0]
+    for i, stage in enumerate(enc, 1):
         if i > 1:
             h = F.max_pool2d(h, 2, 2)
         for j in range(len(stage)):
             h = _vgg_block(p, f"c{i}.{j}", h, training)
         skips.append(h)
-    h = F.conv2d(F.max_pool2d(h, 2, 2), p["c5.0.weight"], p["c5.0.bias"])
-    h = torch.tanh(_bn_train(h, p, "c5.1", training))
+    top = f"c{len(enc) + 1}"
+    h = F.conv2d(F.max_pool2d(h, 2, 2), p[top + ".0.weight"], p[top + ".0.bias"])
+    h = torch.tanh(_bn_train(h, p, top + ".1", training))
     return h.reshape(h.shape[0], -1), skips
 
 
 def vgg_decoder_fwd(p, vec, skips, training=True):
-    """models/vgg_64.py:94-105."""
+    """models/vgg_64.py:94-105, models/vgg_128.py:107-120."""
+    dec = _vgg_lists(_vgg_width(p))[1]
+    n = len(dec)
     d = F.conv_transpose2d(vec.reshape(vec.shape[0], -1, 1, 1), p["upc1.0.weight"], p["upc1.0.bias"])
     d = F.leaky_relu(_bn_train(d, p, "upc1.1", training), LRELU)
-    for i, stage in enumerate(VGG_DEC[:3], 2):
-        d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skips[5 - i]], 1)
+    for i, stage in enumerate(dec[:-1], 2):
+        d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skips[n + 1 - i]], 1)
         for j in range(len(stage)):
             d = _vgg_block(p, f"upc{i}.{j}", d, training)
     d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skips[0]], 1)
-    d = _vgg_block(p, "upc5.0", d, training)
-    return torch.sigmoid(F.conv_transpose2d(d, p["upc5.1.weight"], p["upc5.1.bias"], stride=1, padding=1))
+    last = f"upc{n + 1}"
+    d = _vgg_block(p, last + ".0", d, training)
+    return torch.sigmoid(F.conv_transpose2d(d, p[last + ".1.weight"], p[last + ".1.bias"], stride=1, padding=1))
 
 
 def _residual_linear_container(nin, nout):
@@ -250,8 +269,9 @@ def build_state(cfg: dict, seed: int | None = None, dtype=torch.float32) -> "Ord
         enc = _mlp_encoder_container(51, g, g)
         dec = _mlp_decoder_container(g, 51, g)
     elif cfg.get("backbone") == "vgg":
-        enc = _vgg_encoder_container(g, cfg["channels"])
-        dec = _vgg_decoder_container(g, cfg["channels"])
+        vw = cfg.get("vgg_width", 128 if cfg.get("image_width") == 128 else 64)
+        enc = _vgg_encoder_container(g, cfg["channels"], vw)
+        dec = _vgg_decoder_container(g, cfg["channels"], vw)
     else:
         nc, w = cfg["channels"], cfg["image_width"]
         enc = _dcgan_encoder_container(g, nc, w)

@@ -42,7 +42,8 @@ struct Geom {
   int M;                // GEMM M: kind 0/2: N*H*W pixels; kind 1: Cm
   int Ntot;             // GEMM N: kind 0/2: Cn; kind 1: 16*Cn
   int bh128, bn128;     // pixel box of 128 pixels: {W, bh128, bn128}
-  int bh64, bn64;       // pixel box of 64 pixels (kind 1 K-blocks)
+  int bh64, bn64;       // pixel box of 64 pixels (kind 1 K-blocks): {bw64, bh64, bn64}; bw64 = 64 < W for 128-wide maps
+  int bw64;
   int imgs_per_group;   // addend indexing
   int ks, st, sgn;      // filter taps per side (4 | 3), stride between the two maps (2 | 1), tap-offset sign (+1 | -1)
 };
@@ -143,8 +144,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int q = 0; q < BN / 64; q++)
               tma_load_2d(&tmB, &full_bar[s], sb + q * 64 * 128, (ky * 4 + kx) * g.Cn + n0 + 64 * q, c0);
           } else {
-            int kn0, ky0;
-            pix_block(kb, 64, g.H, g.W, g.bh64, g.bn64, kn0, ky0);
+            int kn0, ky0, kx0 = 0;
+            if (g.bw64 < g.W) {  // a 64-pixel K-block is a fraction of one row
+              const int per_row = g.W / g.bw64;
+              const int rowi = kb / per_row;
+              kx0 = (kb - rowi * per_row) * g.bw64;
+              kn0 = rowi / g.H;
+              ky0 = rowi - kn0 * g.H;
+            } else {
+              pix_block(kb, 64, g.H, g.W, g.bh64, g.bn64, kn0, ky0);
+            }
             const int m0 = mt * BLOCK_M;
             tma_load_2d(&tmA, &full_bar[s], sa, m0, kb * 64);
             tma_load_2d(&tmA, &full_bar[s], sa + 64 * 128, m0 + 64, kb * 64);
@@ -153,7 +162,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int nb = n0 + 64 * q;
               const int tap = nb / g.Cn, c0 = nb - tap * g.Cn;
               const int kh = tap / g.ks, kw = tap - kh * g.ks;
-              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, c0, kw - 1, g.st * ky0 + kh - 1, kn0);
+              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, c0, g.st * kx0 + kw - 1, g.st * ky0 + kh - 1, kn0);
             }
           }
         }
@@ -446,7 +455,16 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   const int taps = g.ks * g.ks;
   if (kind == 3 || kind == 5) kind = 0;
   if (kind == 4) kind = 1;
-  bool ok = box_for(128, H, W, g.bh128, g.bn128) && box_for(64, H, W, g.bh64, g.bn64);
+  // kinds 0 / 2 tile the output in 128-pixel boxes, kind 1 reduces over 64-pixel boxes
+  g.bh128 = g.bn128 = g.bh64 = g.bn64 = 1;
+  g.bw64 = W;
+  bool ok;
+  if (kind == 1) {
+    if (W > 64 && W % 64 == 0 && W * g.st <= 256) { g.bw64 = 64; ok = true; }
+    else ok = box_for(64, H, W, g.bh64, g.bn64);
+  } else {
+    ok = box_for(128, H, W, g.bh128, g.bn128);
+  }
   ok = ok && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
   if (kind == 1) ok = ok && (Cn % 64 == 0) && (Cm % 8 == 0);
   else ok = ok && (Ck % 64 == 0) && (Cn % 32 == 0) && (ldb % 8 == 0);
@@ -487,7 +505,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   g.M = Cm; g.Ntot = taps * Cn; g.Ck = 64;
   rc = map2d(&ta, a, Cm, pix, Cm, 64);  // a_small [pix][Cm] as MN-major A
   if (rc) return rc;
-  rc = map4d(&tb, b, N, g.st * H, g.st * W, Cn, W, g.bh64, g.bn64, g.st);
+  rc = map4d(&tb, b, N, g.st * H, g.st * W, Cn, g.bw64, g.bh64, g.bn64, g.st);
   if (rc) return rc;
   // a wide tile spans several filter taps when Cn == 64; 256-wide tiles pay off while there are few output tiles (measured)
   const bool wide = g.Ntot % 256 == 0 && g_bn256 && (long long)cdiv(Cm, BLOCK_M) * (g.Ntot / 128) <= 64;

@@ -131,8 +131,8 @@ class TrainEngine:
         self.backbone = cfg.get("backbone", "dcgan")
         if self.backbone in ("dcgan", "vgg"):
             self.nc, self.W0 = cfg["channels"], cfg["image_width"]
-            if self.backbone == "vgg":
-                self.W0 = 64  # models/vgg_64.py is 64x64 only
+            if self.backbone == "vgg" and self.W0 not in (64, 128):
+                self.W0 = cfg.get("vgg_width", 64)  # fixtures name the backbone in image_width
             self.chans = [64, 128, 256, 512] if self.W0 == 64 else [64, 128, 256, 512, 512]
             if self.W0 not in (64, 128):
                 raise ValueError("dcgan backbones exist for 64 and 128 pixel frames")

@@ -21,6 +21,9 @@ from .engine import ACT_LRELU, ACT_TANH, BN_MOMENTUM, TrainEngine
 
 VGG_ENC = [[(None, 64), (64, 64)], [(64, 128), (128, 128)], [(128, 256), (256, 256), (256, 256)], [(256, 512), (512, 512), (512, 512)]]
 VGG_DEC = [[(1024, 512), (512, 512), (512, 256)], [(512, 256), (256, 256), (256, 128)], [(256, 128), (128, 64)], [(128, 64)]]
+# models/vgg_128.py:16-105: one more 512-channel stage on both sides
+VGG_ENC_128 = VGG_ENC + [[(512, 512), (512, 512), (512, 512)]]
+VGG_DEC_128 = [[(1024, 512), (512, 512), (512, 512)]] + VGG_DEC
 
 
 def _up8(n):
@@ -30,18 +33,21 @@ def _up8(n):
 class TrainEngineVGG(TrainEngine):
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
-        if self.W0 != 64:
-            raise ValueError("vgg_64 is defined for 64x64 frames")
+        if self.W0 not in (64, 128):
+            raise ValueError("vgg backbones exist for 64x64 (vgg_64) and 128x128 (vgg_128) frames")
+        self.ENC, self.DEC = (VGG_ENC_128, VGG_DEC_128) if self.W0 == 128 else (VGG_ENC, VGG_DEC)
+        self.nst = len(self.ENC)                 # stages; the final 4x4 conv is c{nst+1}, the last decoder block upc{nst+1}
+        self.top, self.last = f"c{self.nst + 1}", f"upc{self.nst + 1}"
         self.ldl = _up8(9 * self.nc)  # row pitch of the last layer's [pix, 9*nc] matrix
 
     # ------------------------------------------------------------------ weights
     def enc_layers(self):
-        for i, stage in enumerate(VGG_ENC):
+        for i, stage in enumerate(self.ENC):
             for j, (cin, cout) in enumerate(stage):
                 yield i, j, (self.nc if cin is None else cin), cout, f"c{i + 1}.{j}.main"
 
     def dec_layers(self):
-        for k, stage in enumerate(VGG_DEC):
+        for k, stage in enumerate(self.DEC):
             for j, (cin, cout) in enumerate(stage):
                 yield k, j, cin, cout, f"upc{k + 2}.{j}.main"
 
@@ -69,7 +75,7 @@ class TrainEngineVGG(TrainEngine):
             P = self.arena["encoder"].p
             for i, j, cin, cout, pre in self.enc_layers():
                 self._pack_conv3(f"enc.{i}.{j}", P[pre + ".0.weight"], cin, 0, cin, cout, want_t=not (i == 0 and j == 0))
-            w = P["c5.0.weight"]
+            w = P[self.top + ".0.weight"]
             wp = self.buf("wp_enc_c5", self.g * 16 * 512)
             K.permute4(w, wp, (self.g, 4, 4, 512), (512 * 16, 4, 1, 16))
             self._packed["enc.c5"] = wp
@@ -93,7 +99,7 @@ class TrainEngineVGG(TrainEngine):
             # ConvTranspose2d(64, nc, 3, 1, 1): Wl[64, (kh,kw,co)] with the row pitch padded to ldl
             nc, ldl = self.nc, self.ldl
             w27 = self.buf("wp_dec_last27", 64 * 9 * nc + 8)
-            K.permute4(P["upc5.1.weight"], w27, (64, 3, 3, nc), (nc * 9, 3, 1, 9))
+            K.permute4(P[self.last + ".1.weight"], w27, (64, 3, 3, nc), (nc * 9, 3, 1, 9))
             wl = self.buf("wp_dec_last", 64 * ldl)
             K.permute4(w27, wl, (64, ldl, 1, 1), (9 * nc, 1, 0, 0))
             self._packed["dec.last"] = wl
@@ -143,7 +149,7 @@ class TrainEngineVGG(TrainEngine):
         K, T, B, nc = self.K, self.T, self.B, self.nc
         P = self.arena["encoder"].p
         N = T * B
-        hw = 64 * 64
+        hw = self.W0 * self.W0
         xs = x.contiguous()
         if nc == 1 and xs.dtype == torch.float32:
             self.x_nhwc = xs.view(-1)  # one channel: NCHW == NHWC, the MSE target is the input itself
@@ -155,8 +161,8 @@ class TrainEngineVGG(TrainEngine):
         else:
             a = self.buf("x_act", N * hw * nc)
             K.permute4(xs, a, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
-        self.venc = [[] for _ in VGG_ENC]
-        H, C = 64, nc
+        self.venc = [[] for _ in self.ENC]
+        H, C = self.W0, nc
         for i, j, cin, cout, pre in self.enc_layers():
             if j == 0 and i > 0:
                 pooled = self.buf(f"venc_pool{i}", N * (H // 2) * (H // 2) * C)
@@ -169,12 +175,12 @@ class TrainEngineVGG(TrainEngine):
             st = self.bn_forward("venc", f"{i}_{j}", raw, y, T, B * H * H, cout, P[pre + ".1.weight"], P[pre + ".1.bias"], ACT_LRELU)
             self.venc[i].append(dict(inp=a, raw=raw, y=y, st=st, cin=cin, cout=cout, H=H, pre=pre))
             a, C = y, cout
-        pooled = self.buf("venc_pool4", N * 16 * 512)
+        pooled = self.buf("venc_pool_top", N * 16 * 512)
         K.maxpool2_fwd(a, pooled, N, 8, 8, 512)
         raw = self.buf("enc_rawf", N * self.g)
         y = self.buf("enc_yf", N * self.g)
-        K.gemm(pooled, self._packed["enc.c5"], raw, N, self.g, 16 * 512, bias=P["c5.0.bias"])
-        st = self.bn_forward("venc", "f", raw, y, T, B, self.g, P["c5.1.weight"], P["c5.1.bias"], ACT_TANH)
+        K.gemm(pooled, self._packed["enc.c5"], raw, N, self.g, 16 * 512, bias=P[self.top + ".0.bias"])
+        st = self.bn_forward("venc", "f", raw, y, T, B, self.g, P[self.top + ".1.weight"], P[self.top + ".1.bias"], ACT_TANH)
         self.enc_final = dict(inp=pooled, raw=raw, y=y, st=st)
         if self.adt == torch.float32:
             self.Hlat = y
@@ -183,7 +189,7 @@ class TrainEngineVGG(TrainEngine):
             K.permute4(y, self.Hlat, (N * self.g, 1, 1, 1), (1, 0, 0, 0))
         ncalls = len(plan.enc_order)
         Bf = self.buffers["encoder"]
-        bns = [(rec["pre"] + ".1", rec["st"]) for recs in self.venc for rec in recs] + [("c5.1", st)]
+        bns = [(rec["pre"] + ".1", rec["st"]) for recs in self.venc for rec in recs] + [(self.top + ".1", st)]
         for bn, s in bns:
             K.bn_ema(Bf[bn + ".running_mean"], Bf[bn + ".running_var"], s["mean"], s["varu"], self.ix["enc_order"], ncalls, s["C"], BN_MOMENTUM)
             Bf[bn + ".num_batches_tracked"] += ncalls
@@ -205,7 +211,7 @@ class TrainEngineVGG(TrainEngine):
         st = self.bn_forward("dec", -1, raw, d, G, B * 16, 512, P["upc1.1.weight"], P["upc1.1.bias"], ACT_LRELU)
         self.dec_first = dict(inp=hp, raw=raw, d=d, st=st)
         nskip = plan.nskip
-        self.vdec = [[] for _ in VGG_DEC]
+        self.vdec = [[] for _ in self.DEC]
         H, C = 4, 512
         a = d
         for k, j, cin, cout, pre in self.dec_layers():
@@ -219,7 +225,7 @@ class TrainEngineVGG(TrainEngine):
             y = self.buf(f"vdec_y{k}_{j}", M * cout)
             rec = dict(inp=a, raw=raw, y=y, cout=cout, H=H, pre=pre, cat=(j == 0), k=k, j=j)
             if j == 0:
-                skip = self.venc[3 - k][-1]["y"]  # frames are a prefix -> the first nskip frames
+                skip = self.venc[self.nst - 1 - k][-1]["y"]  # frames are a prefix -> the first nskip frames
                 addS = self.fbuf(f"vdec_addS{k}", nskip * B * H * H * cout)
                 self.conv3_fwd(skip, self._packed[f"dec.{k}.0.S.wp"], addS, nskip * B, H, C, cout, bias=P[pre + ".0.bias"])
                 self.conv3_fwd(a, self._packed[f"dec.{k}.0.D.wp"], raw, N, H, C, cout, addend=addS, grp_src=self.ix["skip_src"], ipg=B)
@@ -231,11 +237,12 @@ class TrainEngineVGG(TrainEngine):
             self.vdec[k].append(rec)
             a, C = y, cout
         # ConvTranspose2d(64, nc, 3, 1, 1): [pix,64] x [64, 9*nc] GEMM, then the 9-tap gather; the Sigmoid lives in the loss kernel
-        M, ldl = N * 64 * 64, self.ldl
+        W0 = self.W0
+        M, ldl = N * W0 * W0, self.ldl
         colT = self.buf("vdec_colT", M * ldl)
         K.gemm(a, self._packed["dec.last"], colT, M, ldl, 64, b_mn=True)
         raw_out = self.buf("vdec_rawout", M * nc)
-        K.col2im3(colT, raw_out, N, 64, 64, nc, ldl, bias=P["upc5.1.bias"])
+        K.col2im3(colT, raw_out, N, W0, W0, nc, ldl, bias=P[self.last + ".1.bias"])
         self.vlast = dict(inp=a)
         self.dec = [dict(raw=raw_out)]
         Bf = self.buffers["decoder"]
@@ -251,23 +258,24 @@ class TrainEngineVGG(TrainEngine):
         N = Gn * B
         A = self.arena["decoder"]
         nskip = self.last_plan.nskip
-        E = nc * 64 * 64
+        W0 = self.W0
+        E = nc * W0 * W0
         dy = self.d_rawout[g0 * B * E:g1 * B * E]
         # last layer
-        M, ldl = N * 64 * 64, self.ldl
+        M, ldl = N * W0 * W0, self.ldl
         wl = self._packed["dec.last"]
         dcolT = self.buf("vgg_col", M * ldl)
-        K.im2col3(dy, dcolT, N, 64, 64, nc, ldl, 1)
-        x_in = self.vlast["inp"][g0 * B * 4096 * 64:g1 * B * 4096 * 64]
+        K.im2col3(dy, dcolT, N, W0, W0, nc, ldl, 1)
+        x_in = self.vlast["inp"][g0 * B * W0 * W0 * 64:g1 * B * W0 * W0 * 64]
         dd = self.buf("vdec_gd_last", M * 64)
         K.gemm(dcolT, wl, dd, M, 64, ldl)
         if want_wgrad:
-            K.colsum(dy, M, nc, nc, A.g["upc5.1.bias"])
+            K.colsum(dy, M, nc, nc, A.g[self.last + ".1.bias"])
             gwl = self.fbuf("gwp_dec_last", 64 * ldl)
             K.gemm(x_in, dcolT, gwl, 64, ldl, M, a_mn=True, b_mn=True, lda=64, ldb=ldl)
-            K.permute4(gwl, A.g["upc5.1.weight"], (64, nc, 3, 3), (ldl, 1, 3 * nc, nc))
+            K.permute4(gwl, A.g[self.last + ".1.weight"], (64, nc, 3, 3), (ldl, 1, 3 * nc, nc))
         dy = dd
-        for k in range(len(VGG_DEC) - 1, -1, -1):
+        for k in range(self.nst - 1, -1, -1):
             for rec in reversed(self.vdec[k]):
                 cout, cin, H, pre, j = rec["cout"], rec["cin"], rec["H"], rec["pre"], rec["j"]
                 st = rec["st"]
@@ -343,21 +351,21 @@ class TrainEngineVGG(TrainEngine):
         fin = self.enc_final
         st = fin["st"]
         K.bn_bwd(dy, fin["raw"], fin["y"], st["mean"], st["invstd"], st["gamma"], T, B, g, ACT_TANH, dy, st["sdz"], st["sdzx"])
-        K.bn_param_grad(st["sdz"], st["sdzx"], T, g, A.g["c5.1.weight"], A.g["c5.1.bias"])
-        A.g["c5.0.bias"].zero_()
+        K.bn_param_grad(st["sdz"], st["sdzx"], T, g, A.g[self.top + ".1.weight"], A.g[self.top + ".1.bias"])
+        A.g[self.top + ".0.bias"].zero_()
         gw = self.fbuf("gwp_enc_c5", g * 16 * 512)
         K.gemm(dy, fin["inp"], gw, g, 16 * 512, N, a_mn=True, b_mn=True, lda=g, ldb=16 * 512)
-        K.permute4(gw, A.g["c5.0.weight"], (g, 512, 4, 4), (16 * 512, 1, 4 * 512, 512))
+        K.transpose_batched(gw, A.g[self.top + ".0.weight"], g, 16, 512)
         gy = self.buf("venc_gpool4", N * 16 * 512)
         K.gemm(dy, self._packed["enc.c5"], gy, N, 16 * 512, g, b_mn=True)
-        for i in range(len(VGG_ENC) - 1, -1, -1):
+        for i in range(self.nst - 1, -1, -1):
             recs = self.venc[i]
             top = recs[-1]
             H, C = top["H"], top["cout"]
             # MaxPool backward into this stage's output, plus the skip gradient from the decoder stage that consumed it
             gyo = self.buf(f"venc_gy{i}", N * H * H * C)
             K.maxpool2_bwd(top["y"], gy, gyo, N, H, H, C)
-            dsk = self.vdec[3 - i][0].get("dskip")
+            dsk = self.vdec[self.nst - 1 - i][0].get("dskip")
             if dsk is not None:
                 K.add_indexed(gyo, dsk, self.ix["skip_dst"], nskip, B * H * H * C)
             gy = gyo

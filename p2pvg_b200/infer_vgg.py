@@ -53,12 +53,13 @@ def vgg_encoder_forward(mod, x):
     dev, adt = x.device, _act_dtype()
     K.set_fp32_gemm_mode(0)
     B, nc, H = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
-    if H != 64 or int(x.shape[3]) != 64:
-        raise ValueError("vgg_64 expects 64x64 frames")
+    if H != mod.image_width or int(x.shape[3]) != mod.image_width:
+        raise ValueError(f"this vgg backbone expects {mod.image_width}x{mod.image_width} frames")
+    nst = mod.nstage
     a = torch.empty(B * H * H * nc, device=dev, dtype=adt)
     K.permute4(x.contiguous().float(), a, (B, H * H, nc, 1), (nc * H * H, 1, H * H, 0))
     skips, C = [], nc
-    for i in range(1, 5):
+    for i in range(1, nst + 1):
         if i > 1:
             p = torch.empty(B * (H // 2) * (H // 2) * C, device=dev, dtype=adt)
             K.maxpool2_fwd(a, p, B, H, H, C)
@@ -71,7 +72,8 @@ def vgg_encoder_forward(mod, x):
         skips.append(nchw)
     p = torch.empty(B * 16 * C, device=dev, dtype=adt)
     K.maxpool2_fwd(a, p, B, H, H, C)
-    conv, bn = mod.c5[0], mod.c5[1]
+    top = getattr(mod, f"c{nst + 1}")
+    conv, bn = top[0], top[1]
     g = mod.dim
     wp = torch.empty(g * 16 * C, device=dev, dtype=adt)
     K.permute4(conv.weight.data, wp, (g, 4, 4, C), (C * 16, 4, 1, 16))
@@ -104,30 +106,31 @@ def vgg_decoder_forward(mod, vec, skip):
     K.gemm(hp, wp, raw, B, 16 * 512, g, b_mn=True, bias=b16)
     _bn(K, bn, raw, d, 1, B * 16, 512, ACT_LRELU, dev)
     H, C = 4, 512
-    for k in range(4):
+    nst, W0 = mod.nstage, mod.image_width
+    for k in range(nst):
         H *= 2
         u = torch.empty(B * H * H * C, device=dev, dtype=adt)
         K.upsample2_fwd(d, u, B, H // 2, H // 2, C)
-        sk = _to_nhwc(K, skip[3 - k], adt)
+        sk = _to_nhwc(K, skip[nst - 1 - k], adt)
         blocks = list(getattr(mod, f"upc{k + 2}"))
-        layers = blocks if k < 3 else blocks[:1]
+        layers = blocks if k < nst - 1 else blocks[:1]
         d, C = _layer(K, layers[0], u, B, H, adt, dev, extra=sk)
         for blk in layers[1:]:
             d, C = _layer(K, blk, d, B, H, adt, dev)
-    convt = mod.upc5[1]
+    convt = getattr(mod, f"upc{nst + 1}")[1]
     ldl = _up8(9 * nc)
     w27 = torch.zeros(64 * 9 * nc + 8, device=dev, dtype=adt)
     K.permute4(convt.weight.data, w27, (64, 3, 3, nc), (nc * 9, 3, 1, 9))
     wl = torch.empty(64 * ldl, device=dev, dtype=adt)
     K.permute4(w27, wl, (64, ldl, 1, 1), (9 * nc, 1, 0, 0))
-    M = B * 64 * 64
+    M = B * W0 * W0
     colT = torch.empty(M * ldl, device=dev, dtype=adt)
     K.gemm(d, wl, colT, M, ldl, 64, b_mn=True)
     raw = torch.empty(M * nc, device=dev, dtype=adt)
-    K.col2im3(colT, raw, B, 64, 64, nc, ldl, bias=convt.bias.data)
+    K.col2im3(colT, raw, B, W0, W0, nc, ldl, bias=convt.bias.data)
     out32 = torch.empty(M * nc, device=dev)
     K.permute4(raw, out32, (M * nc, 1, 1, 1), (1, 0, 0, 0))
     K.act_fwd(out32, M * nc, ACT_SIGMOID)
-    out = torch.empty(B, nc, 64, 64, device=dev)
-    K.permute4(out32, out, (B, nc, 64 * 64, 1), (64 * 64 * nc, 1, nc, 0))
+    out = torch.empty(B, nc, W0, W0, device=dev)
+    K.permute4(out32, out, (B, nc, W0 * W0, 1), (W0 * W0 * nc, 1, nc, 0))
     return out

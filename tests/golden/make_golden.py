@@ -86,10 +86,12 @@ def import_reference():
     import models.dcgan_128 as d128
     import models.h36m_mlp as mlp
     import models.vgg_64 as vgg64
+    import models.vgg_128 as vgg128
     backbones[64] = d64
     backbones[128] = d128
     backbones["mlp"] = mlp
     backbones["vgg"] = vgg64
+    backbones["vgg128"] = vgg128
     return p2p_model, backbones
 
 
@@ -112,6 +114,8 @@ CASES = {
     "d64_cfgbatch": dict(width=64, channels=1, T=4, B=2, steps=1, opt=dict(batch_size=5), np_seed=2),
     # vgg_64 backbone (models/vgg_64.py), 3-channel frames (weizmann shape)
     "vgg64_rgb": dict(width="vgg", channels=3, T=4, B=2, steps=1, opt={}, np_seed=6),
+    # vgg_128 backbone (models/vgg_128.py), 1-channel 128x128 frames
+    "vgg128_gray": dict(width="vgg128", channels=1, T=3, B=2, steps=1, opt={}, np_seed=8),
     # human3.6m pose backbone (models/h36m_mlp.py): x is the tuple (pose_2d, pose_3d, camera_view), MSE on [B,17,3]
     "h36m_mlp": dict(width="mlp", channels=1, T=7, B=4, steps=1, opt=dict(dataset="h36m", skip_prob=0.3), np_seed=4),
 }
@@ -130,8 +134,9 @@ def run_case(name, spec, p2p_model, backbones):
     mods = dict(frame_predictor=model.frame_predictor, posterior=model.posterior, prior=model.prior,
                 encoder=model.encoder, decoder=model.decoder)
     fix = dict(case=name, cfg=dict(g_dim=g_dim, z_dim=z_dim, rnn_size=rnn, channels=spec["channels"],
-                                   image_width=spec["width"], predictor_rnn_layers=2, posterior_rnn_layers=1,
-                                   prior_rnn_layers=1, backbone=(spec["width"] if spec["width"] in ("mlp", "vgg") else "dcgan")),
+                                   image_width=("vgg" if spec["width"] == "vgg128" else spec["width"]), vgg_width=(128 if spec["width"] == "vgg128" else 64),
+                                   predictor_rnn_layers=2, posterior_rnn_layers=1,
+                                   prior_rnn_layers=1, backbone=({"mlp": "mlp", "vgg": "vgg", "vgg128": "vgg"}.get(spec["width"], "dcgan"))),
                opt={k: getattr(opt, k) for k in ("beta", "weight_cpc", "weight_align", "skip_prob", "n_past",
                                                  "last_frame_skip", "lr", "beta1", "batch_size")},
                init_seed=1, torch=torch.__version__)
@@ -162,7 +167,7 @@ def run_case(name, spec, p2p_model, backbones):
         if W == "mlp":
             x = torch.randn(T, B, 17, 3, generator=gen)
         else:
-            side = 64 if W == "vgg" else W
+            side = {"vgg": 64, "vgg128": 128}.get(W, W)
             x = torch.rand(T, B, C, side, side, generator=gen)
         np.random.seed(spec["np_seed"] + step)
         probs = np.random.uniform(0, 1, T - 1)

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_dropin_packages_resolve_to_the_kernel_backed_modules():
-    code = ("import models.dcgan_64 as b, models.dcgan_128, models.vgg_64, models.h36m_mlp, models.lstm as l; from models.p2p_model import P2PModel; "
+    code = ("import models.dcgan_64 as b, models.dcgan_128, models.vgg_64, models.vgg_128, models.h36m_mlp, models.lstm as l; from models.p2p_model import P2PModel; "
             "from misc import criterion; import p2pvg_b200.models.p2p_model as impl; "
             "assert P2PModel is impl.P2PModel and hasattr(b, 'encoder') and hasattr(l, 'gaussian_lstm'); "
             "assert criterion.KLCriterion.__module__.startswith('p2pvg_b200'); print('ok')")
