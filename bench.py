@@ -6,8 +6,9 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  `value` = device-timed throughput with the batch resident in HBM;
-`e2e` = the same through the public drop-in API (models.p2p_model.P2PModel.__call__) with the batch copied
-from pinned host memory and the four loss scalars read back every step; `roofline` = the tcgen05 GEMM
+`e2e` = the same through the public drop-in API (p2pvg_b200.data.DevicePrefetcher feeding
+models.p2p_model.P2PModel.__call__): every step's batch is copied from pinned host memory inside the timed
+region (side stream, overlapping the previous step) and the four loss scalars are read back every step; `roofline` = the tcgen05 GEMM
 kernel (executed FLOPs / CUDA-event time of its launches, measured in an instrumented pass inside this
 process); `cpu_baseline` = the CPU oracle (port of the reference path) on the host cores.
 `--impl reference` times the reference's CPU path (the oracle port; the reference itself is pure PyTorch
