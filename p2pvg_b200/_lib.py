@@ -68,8 +68,9 @@ class CudaKernels:
         if not torch.cuda.is_available():
             raise RuntimeError("p2pvg_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda")
-        self._gemm_ws = None
-        self._bn_ws = None
+        self._gemm_ws = {}
+        self._bn_ws = {}
+        self.lane = 0   # workspace set in use: the engine switches to lane 1 for work enqueued on its side stream
         self.launches = 0
 
     # -- helpers ---------------------------------------------------------------------------
@@ -82,15 +83,17 @@ class CudaKernels:
             raise KernelError(f"p2pvg_b200 error {rc}: {self.lib.p2pvg_last_error().decode()}")
 
     def gemm_workspace(self):
-        if self._gemm_ws is None:
-            self._gemm_ws = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
-        return self._gemm_ws
+        ws = self._gemm_ws.get(self.lane)
+        if ws is None:
+            ws = self._gemm_ws[self.lane] = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+        return ws
 
     def bn_workspace(self, G, C):
         need = self.lib.p2pvg_bn_workspace_bytes(_i(G), _i(C))
-        if self._bn_ws is None or self._bn_ws.numel() < need:
-            self._bn_ws = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=self.device)
-        return self._bn_ws
+        ws = self._bn_ws.get(self.lane)
+        if ws is None or ws.numel() < need:
+            ws = self._bn_ws[self.lane] = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=self.device)
+        return ws
 
     def set_gemm_impl(self, impl: str):
         self._ck(self.lib.p2pvg_set_gemm_impl(_i({"auto": 0, "simt": 1, "tc": 2}[impl])))

@@ -162,8 +162,47 @@ class TrainEngine:
         # 1/3-channel ends (K = 16 nc or N = 16 nc < 64): four pixel rows are multiplied as one row against a block-diagonal
         # copy of the weight, so that no TMA box is out of bounds (measured 3x faster than the partially-OOB boxes)
         self.bd = (act_dtype == torch.bfloat16) and hasattr(kernels, "blockdiag") and os.environ.get("P2PVG_BLOCKDIAG", "1") != "0"
+        # weight gradients and the skip-path of the backward pass are off the critical path: they are enqueued on a side
+        # stream (captured into the same CUDA graph) so that the TMA-bound wgrad GEMMs overlap the HBM-bound BatchNorm kernels
+        # and the latency-bound LSTM scans of the main stream.  Measured gain on one B200: 1.3 % (24.57 -> 24.26 ms) -- the
+        # persistent GEMMs leave little room for a co-resident kernel -- so it is opt-in: P2PVG_OVERLAP=1.
+        self.overlap = getattr(kernels, "name", "") == "cuda" and os.environ.get("P2PVG_OVERLAP", "0") == "1"
+        self.side = None
+        self._side_dirty = False
         self.last_plan = None
         self.phase_events = None
+
+    # ------------------------------------------------------------------ side stream
+    def fork(self):
+        """Context manager: kernels enqueued inside run on the side stream, after everything enqueued on the main stream so far."""
+        import contextlib
+        if not self.overlap or self.phase_events is not None:
+            return contextlib.nullcontext()
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.dev)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side.wait_event(ev)
+        self._side_dirty = True
+        eng = self
+
+        @contextlib.contextmanager
+        def ctx():
+            eng.K.lane = 1
+            try:
+                with torch.cuda.stream(eng.side):
+                    yield
+            finally:
+                eng.K.lane = 0
+        return ctx()
+
+    def join(self):
+        """The main stream waits for everything enqueued on the side stream."""
+        if self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_dirty = False
 
     # ------------------------------------------------------------------ memory
     def buf(self, name, numel, dtype=None):
@@ -660,18 +699,22 @@ class TrainEngine:
                 gw = self.fbuf(f"gwp_dec{k}", 2 * cd * 16 * cout)
             if rec["imp"]:
                 # data gradient = stride-2 conv of dy; weight gradients gather dy by filter tap; the skip half works
-                # on dy summed over the calls that share a skip frame (conv is linear) -- no col buffers at all
-                K.conv_gemm(0, dy, wD, dd, N, Hi, Hi, cout, cd)
-                if want_wgrad:
-                    K.conv_gemm(1, x_in, dy, gw[:cd * 16 * cout], N, Hi, Hi, 0, cout, Cm=cd)
-                if want_skip:
-                    dyS = self.buf("scratch_dyS", nskip * B * Ho * Ho * cout)
-                    K.group_sum(dy, dyS, self.ix["skip_src"][g0:g1], Gn, nskip, B * Ho * Ho * cout)
-                    dsk = self.buf(f"dskip{k}", Ms * cd)
-                    K.conv_gemm(0, dyS, wS, dsk, nskip * B, Hi, Hi, cout, cd)
-                    rec["dskip"] = dsk
+                # on dy summed over the calls that share a skip frame (conv is linear) -- no col buffers at all.
+                # Only the data gradient is on the critical path: everything else goes to the side stream.
+                with self.fork():
                     if want_wgrad:
-                        K.conv_gemm(1, rec["skip"], dyS, gw[cd * 16 * cout:], nskip * B, Hi, Hi, 0, cout, Cm=cd)
+                        K.conv_gemm(1, x_in, dy, gw[:cd * 16 * cout], N, Hi, Hi, 0, cout, Cm=cd)
+                    if want_skip:
+                        dyS = self.buf(f"scratch_dyS{k}", nskip * B * Ho * Ho * cout)
+                        K.group_sum(dy, dyS, self.ix["skip_src"][g0:g1], Gn, nskip, B * Ho * Ho * cout)
+                        dsk = self.buf(f"dskip{k}", Ms * cd)
+                        K.conv_gemm(0, dyS, wS, dsk, nskip * B, Hi, Hi, cout, cd)
+                        rec["dskip"] = dsk
+                        if want_wgrad:
+                            K.conv_gemm(1, rec["skip"], dyS, gw[cd * 16 * cout:], nskip * B, Hi, Hi, 0, cout, Cm=cd)
+                    if want_wgrad:
+                        K.transpose_batched(gw, A.g[cn + ".weight"], 2 * cd, 16, cout)   # [2cd][tap][co] -> [2cd][co][tap]
+                K.conv_gemm(0, dy, wD, dd, N, Hi, Hi, cout, cd)
             elif rec["thin"]:
                 w32 = A.p[cn + ".weight"]
                 K.conv_thin_in(dy, w32[:cd], None, dd, N, Ho, Ho, cout, cd)   # data gradient: the ConvT weight is a conv weight [cd][nc][4][4]
@@ -710,7 +753,7 @@ class TrainEngine:
                     rec["dskip"] = dsk
                     if want_wgrad:
                         K.gemm(rec["skip"], dcolS, gw[cd * 16 * cout:], cd, 16 * cout, Ms, a_mn=True, b_mn=True, lda=cd, ldb=16 * cout)
-            if want_wgrad:
+            if want_wgrad and not rec["imp"]:
                 K.transpose_batched(gw, A.g[cn + ".weight"], 2 * cd, 16, cout)   # [2cd][tap][co] -> [2cd][co][tap]
             dy = dd
         # upc1: BatchNorm + LeakyReLU, then the g -> 4x4xCtop GEMM
@@ -868,6 +911,7 @@ class TrainEngine:
         A = self.arena["encoder"]
         N = T * B
         nskip = plan.nskip
+        self.join()   # the skip gradients of the decoder come from the side stream
         if self.adt == torch.float32:
             dy = self.dH
         else:
@@ -900,14 +944,17 @@ class TrainEngine:
             A.g[cn + ".bias"].zero_()
             gw = self.fbuf(f"gwp_enc{l}", cout * 16 * cin)
             if rec["imp"]:
-                K.conv_gemm(1, gy, rec["inp"], gw, N, Ho, Ho, 0, cin, Cm=cout)
+                with self.fork():   # off the critical path
+                    K.conv_gemm(1, gy, rec["inp"], gw, N, Ho, Ho, 0, cin, Cm=cout)
+                    K.transpose_batched(gw, A.g[cn + ".weight"], cout, 16, cin)   # [co][tap][ci] -> [co][ci][tap]
             else:
                 col = rec["col"]
                 if col is None:  # thin first layer: the im2col matrix is only needed here
                     col = self.buf(f"enc_col{l}", M * 16 * cin)
                     K.im2col(rec["inp"], col, N, rec["Hin"], rec["Hin"], cin)
                 K.gemm(gy, col, gw, cout, 16 * cin, M, a_mn=True, b_mn=True, lda=cout, ldb=16 * cin)
-            K.transpose_batched(gw, A.g[cn + ".weight"], cout, 16, cin)   # [co][tap][ci] -> [co][ci][tap]
+            if not rec["imp"]:
+                K.transpose_batched(gw, A.g[cn + ".weight"], cout, 16, cin)   # [co][tap][ci] -> [co][ci][tap]
             if l > 0:
                 gprev = self.buf(f"enc_gy{l - 1}", N * rec["Hin"] * rec["Hin"] * cin)
                 if rec["imp"]:
@@ -957,6 +1004,7 @@ class TrainEngine:
     # -- optimiser --------------------------------------------------------------------------
     def adam(self, modules):
         opt = self.opt
+        self.join()   # weight gradients produced on the side stream
         if self.dist is not None:
             # data parallel: replicas hold batch shards; average the flat gradient arenas over NVLink (NCCL)
             dist, group, world = self.dist
