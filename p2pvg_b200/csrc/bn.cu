@@ -17,7 +17,7 @@ __device__ __forceinline__ float act_grad(float y, int act) {
 // MODE 0: (sum x, sum x^2).  MODE 1: (sum dz, sum dz*xhat), dz = dy*act'(y), xhat=(x-mean)*invstd
 // 16-byte vectors along the channel axis (V = 8 bf16 / 4 fp32 channels per thread), 256/CV row lanes per block.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                                                         long long R, int C, int rows_per_chunk, double2* __restrict__ partial,
                                                         const float* __restrict__ scale, const float* __restrict__ shift) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const T* __restrict__ x, T*
 // grid (chunk, group); thread = (channel vector cv, row lane): the per-(group,channel) parameters stay in registers
 // and only the activations stream through.
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ sum_dz,
                                                            const float* __restrict__ sum_dzx, long long R, int C, int rows_per_chunk,
