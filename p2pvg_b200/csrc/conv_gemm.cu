@@ -112,15 +112,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int ph = t / (tiles_mn * splits);           // output-parity phase (kind 2)
+        // tile decode with as few integer divisions as possible: the producer thread is the latency-critical one
+        const int ph = (KIND == 2) ? t / tiles_mn : 0;    // output-parity phase (kind 2; kinds 0 / 2 never split K)
         const int t2 = t - ph * tiles_mn * splits;
-        const int z = t2 / tiles_mn, r = t2 - z * tiles_mn;
-        const int mt = r / tiles_n, nt = r % tiles_n;
+        const int z = (splits == 1) ? 0 : t2 / tiles_mn, r = t2 - z * tiles_mn;
+        const int mt = (tiles_n == 1) ? r : r / tiles_n, nt = (tiles_n == 1) ? 0 : r - mt * tiles_n;
         const int n0 = nt * BN;
         const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
         int pn0 = 0, py0 = 0;
         if (KIND != 1) pix_block(mt, 128, g.H, g.W, g.bh128, g.bn128, pn0, py0);
         const int pa = ph >> 1, pb_ = ph & 1;
+        // kind 1: everything that does not depend on the K-block is computed once per tile, the pixel-box coordinates
+        // advance incrementally -- the single producer thread must not spend its K-block budget on integer divisions
+        int kn0 = 0, ky0 = 0, kx0 = 0;
+        int t_kh = 0, t_kw = 0, t_cc = 0;
+        int qc0[BN / 64], qdx[BN / 64], qdy[BN / 64];
+        if (KIND == 1) {
+          if (g.bw64 < g.W) {  // a 64-pixel K-block is a fraction of one row
+            const int per_row = g.W / g.bw64;
+            const int rowi = kb0 / per_row;
+            kx0 = (kb0 - rowi * per_row) * g.bw64;
+            kn0 = rowi / g.H;
+            ky0 = rowi - kn0 * g.H;
+          } else {
+            pix_block(kb0, 64, g.H, g.W, g.bh64, g.bn64, kn0, ky0);
+          }
+#pragma unroll
+          for (int q = 0; q < BN / 64; q++) {
+            const int nb = n0 + 64 * q;
+            const int tap = nb / g.Cn;
+            const int kh = tap / g.ks;
+            qc0[q] = nb - tap * g.Cn;
+            qdx[q] = tap - kh * g.ks - 1;
+            qdy[q] = kh - 1;
+          }
+        }
         for (int kb = kb0; kb < kb1; kb++, it++) {
           const int s = it % C_::STAGES;
           const uint32_t par = (it / C_::STAGES) & 1;
@@ -129,12 +155,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
           if (KIND == 0) {
-            const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * 64;
-            const int kh = tap / g.ks, kw = tap - kh * g.ks;
-            tma_load_4d(&tmA, &full_bar[s], sa, c0, g.sgn * (kw - 1), g.st * py0 + g.sgn * (kh - 1), pn0);
-            tma_load_2d(&tmB, &full_bar[s], sb, tap * g.Ck + c0, n0);
+            // (kh, kw, channel chunk) advance incrementally (kinds 0 / 2 never split K: kb starts at 0)
+            tma_load_4d(&tmA, &full_bar[s], sa, t_cc * 64, g.sgn * (t_kw - 1), g.st * py0 + g.sgn * (t_kh - 1), pn0);
+            tma_load_2d(&tmB, &full_bar[s], sb, kb * 64, n0);   // (tap * Ck + c0) == kb * 64
+            if (++t_cc == cchunks) { t_cc = 0; if (++t_kw == g.ks) { t_kw = 0; t_kh++; } }
           } else if (KIND == 2) {
-            const int tq = kb / cchunks, c0 = (kb - tq * cchunks) * 64;
+            const int tq = t_kh, c0 = t_cc * 64;   // t_kh doubles as the 2x2 tap index of this phase
+            if (++t_cc == cchunks) { t_cc = 0; t_kh++; }
             const int i = tq >> 1, j = tq & 1;
             // phase a: taps (dy=0, ky=a+1) and (dy = a ? +1 : -1, ky = a ? 0 : 3); same along x
             const int dy = i == 0 ? 0 : (pa ? 1 : -1), ky = i == 0 ? pa + 1 : (pa ? 0 : 3);
@@ -144,25 +171,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int q = 0; q < BN / 64; q++)
               tma_load_2d(&tmB, &full_bar[s], sb + q * 64 * 128, (ky * 4 + kx) * g.Cn + n0 + 64 * q, c0);
           } else {
-            int kn0, ky0, kx0 = 0;
-            if (g.bw64 < g.W) {  // a 64-pixel K-block is a fraction of one row
-              const int per_row = g.W / g.bw64;
-              const int rowi = kb / per_row;
-              kx0 = (kb - rowi * per_row) * g.bw64;
-              kn0 = rowi / g.H;
-              ky0 = rowi - kn0 * g.H;
-            } else {
-              pix_block(kb, 64, g.H, g.W, g.bh64, g.bn64, kn0, ky0);
-            }
             const int m0 = mt * BLOCK_M;
             tma_load_2d(&tmA, &full_bar[s], sa, m0, kb * 64);
             tma_load_2d(&tmA, &full_bar[s], sa + 64 * 128, m0 + 64, kb * 64);
 #pragma unroll
-            for (int q = 0; q < BN / 64; q++) {
-              const int nb = n0 + 64 * q;
-              const int tap = nb / g.Cn, c0 = nb - tap * g.Cn;
-              const int kh = tap / g.ks, kw = tap - kh * g.ks;
-              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, c0, g.st * kx0 + kw - 1, g.st * ky0 + kh - 1, kn0);
+            for (int q = 0; q < BN / 64; q++)
+              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, qc0[q], g.st * kx0 + qdx[q], g.st * ky0 + qdy[q], kn0);
+            // next 64-pixel box
+            if (g.bw64 < g.W) {
+              kx0 += g.bw64;
+              if (kx0 >= g.W) { kx0 = 0; if (++ky0 >= g.H) { ky0 = 0; kn0++; } }
+            } else if (g.H * g.W >= 64) {
+              ky0 += g.bh64;
+              if (ky0 >= g.H) { ky0 = 0; kn0++; }
+            } else {
+              kn0 += g.bn64;
             }
           }
         }
@@ -175,9 +198,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
-        const int ph = t / (tiles_mn * splits);
-        const int t2 = t - ph * tiles_mn * splits;
-        const int z = t2 / tiles_mn;
+        int z = 0;
+        if (splits > 1) {
+          const int ph = t / (tiles_mn * splits);
+          const int t2 = t - ph * tiles_mn * splits;
+          z = t2 / tiles_mn;
+        }
         const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
         const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
@@ -207,10 +233,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __shared__ float bias_s[2 * BN];
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
-      const int ph = t / (tiles_mn * splits);
+      const int ph = (KIND == 2) ? t / tiles_mn : 0;
       const int t2 = t - ph * tiles_mn * splits;
-      const int z = t2 / tiles_mn, r = t2 - z * tiles_mn;
-      const int mt = r / tiles_n, nt = r % tiles_n;
+      const int z = (splits == 1) ? 0 : t2 / tiles_mn, r = t2 - z * tiles_mn;
+      const int mt = (tiles_n == 1) ? r : r / tiles_n, nt = (tiles_n == 1) ? 0 : r - mt * tiles_n;
       const int n0 = nt * BN;
       const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
       const int rt = q * 32 + lane;  // row within the tile

@@ -182,8 +182,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int z = t / tiles_mn, r = t - z * tiles_mn;
-        const int m0 = (r / tiles_n) * BLOCK_M, n0 = (r % tiles_n) * BN;
+        const int z = (splits == 1) ? 0 : t / tiles_mn, r = t - z * tiles_mn;   // fast path: no integer division without split-K
+        const int mt_ = (tiles_n == 1) ? r : r / tiles_n;
+        const int m0 = mt_ * BLOCK_M, n0 = (r - mt_ * tiles_n) * BN;
         const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
         for (int kb = kb0; kb < kb1; kb++, it++) {
           const int s = it % C_::STAGES;
@@ -217,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
-        const int z = t / tiles_mn;
+        const int z = (splits == 1) ? 0 : t / tiles_mn;
         const int kb0 = z * kb_per_split, kb1 = min(kb0 + kb_per_split, nkb_total);
         const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
@@ -251,8 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ float bias_s[2 * BN];
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
-      const int z = t / tiles_mn, r = t - z * tiles_mn;
-      const int m0 = (r / tiles_n) * BLOCK_M, n0 = (r % tiles_n) * BN;
+      const int z = (splits == 1) ? 0 : t / tiles_mn, r = t - z * tiles_mn;   // fast path: no integer division without split-K
+      const int mt_ = (tiles_n == 1) ? r : r / tiles_n;
+        const int m0 = mt_ * BLOCK_M, n0 = (r - mt_ * tiles_n) * BN;
       const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
       const long long m = (long long)m0 + q * 32 + lane;
       const bool row_ok = m < M;
