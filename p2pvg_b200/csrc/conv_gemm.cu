@@ -386,6 +386,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_enc = nullptr;
 std::once_flag g_once2;
 int g_sms = 148;
+int g_k1_wide_max = 1 << 30;  // kind 1: 256-wide tiles while there are at most this many 128-wide output tiles (P2PVG_K1_WIDE_MAX)
 int g_bn256 = 1;  // P2PVG_CONV_BN256=0 keeps the 128-wide tiles (A/B comparison)
 int g_attr[3][3] = {};
 
@@ -399,6 +400,8 @@ void resolve2() {
   (void)cudaGetLastError();
   const char* e = getenv("P2PVG_CONV_BN256");
   if (e != nullptr && e[0] == '0') g_bn256 = 0;
+  const char* w = getenv("P2PVG_K1_WIDE_MAX");
+  if (w != nullptr) g_k1_wide_max = atoi(w);
 }
 
 int map2d(CUtensorMap* m, const void* base, long long dim0, long long dim1, long long ld, int box1) {
@@ -534,7 +537,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   rc = map4d(&tb, b, N, g.st * H, g.st * W, Cn, g.bw64, g.bh64, g.bn64, g.st);
   if (rc) return rc;
   // a wide tile spans several filter taps when Cn == 64; 256-wide tiles pay off while there are few output tiles (measured)
-  const bool wide = g.Ntot % 256 == 0 && g_bn256 && (long long)cdiv(Cm, BLOCK_M) * (g.Ntot / 128) <= 64;
+  const bool wide = g.Ntot % 256 == 0 && g_bn256 && (long long)cdiv(Cm, BLOCK_M) * (g.Ntot / 128) <= g_k1_wide_max;
   const int BN = wide ? 256 : (g.Ntot % 128 == 0) ? 128 : 64;
   const int nkb = (int)((pix + 63) / 64);
   const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(g.Ntot, BN);
