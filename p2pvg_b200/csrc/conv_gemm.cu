@@ -308,8 +308,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (KIND == 1 && partial != nullptr) {
             float* dst = partial + ((long long)z * g.M + out_row) * g.Ntot + nbase;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            for (int j = 0; j < 32; j += 8)   // partial workspace rows are 32-byte aligned (Ntot and nbase are multiples of 32)
+              st_global_256(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
             continue;
           }
           float f[32];
@@ -336,16 +336,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; j++) f[j] += __bfloat162float(crow[j]);
             }
+            if ((reinterpret_cast<uintptr_t>(crow) & 31) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&p0);
-              pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2);
-              pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(crow + j) = pk;
+              for (int j = 0; j < 32; j += 16)
+                st_global_256(crow + j, pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]), pack_bf16x2(f[j + 4], f[j + 5]),
+                              pack_bf16x2(f[j + 6], f[j + 7]), pack_bf16x2(f[j + 8], f[j + 9]), pack_bf16x2(f[j + 10], f[j + 11]),
+                              pack_bf16x2(f[j + 12], f[j + 13]), pack_bf16x2(f[j + 14], f[j + 15]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                pk.x = pack_bf16x2(f[j], f[j + 1]);
+                pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
+                pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(crow + j) = pk;
+              }
             }
           } else {
             float* crow = reinterpret_cast<float*>(Cv) + out_row * ldc + nbase;
@@ -353,8 +359,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; j++) f[j] += crow[j];
             }
+            if ((reinterpret_cast<uintptr_t>(crow) & 31) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              for (int j = 0; j < 32; j += 8)
+                st_global_256(crow + j, __float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]), __float_as_uint(f[j + 3]),
+                              __float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]), __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
           }
         }
       }

@@ -108,6 +108,17 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* v) {
                :
                : "memory");
 }
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per instruction -- the thread-per-row epilogues would
+// otherwise write every sector in two 16-byte halves
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
+                                              uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 // named barrier among the four epilogue warps (barrier 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -324,16 +335,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (nbase + j < N) f[j] += __bfloat162float(crow[j]);
             }
             const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-            if (vec) {
+            if (vec && (reinterpret_cast<uintptr_t>(crow) & 31) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 16)
+                st_global_256(crow + j, pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]), pack_bf16x2(f[j + 4], f[j + 5]),
+                              pack_bf16x2(f[j + 6], f[j + 7]), pack_bf16x2(f[j + 8], f[j + 9]), pack_bf16x2(f[j + 10], f[j + 11]),
+                              pack_bf16x2(f[j + 12], f[j + 13]), pack_bf16x2(f[j + 14], f[j + 15]));
+            } else if (vec) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 pk;
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&p0);
-                pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                pk.z = *reinterpret_cast<uint32_t*>(&p2);
-                pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                pk.x = pack_bf16x2(f[j], f[j + 1]);
+                pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
+                pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
                 *reinterpret_cast<uint4*>(crow + j) = pk;
               }
             } else {
@@ -355,7 +370,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (nbase + j < N) f[j] += crow[j];
             }
             const bool vec = (nbase + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-            if (vec) {
+            if (vec && (reinterpret_cast<uintptr_t>(crow) & 31) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                st_global_256(crow + j, __float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]), __float_as_uint(f[j + 3]),
+                              __float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]), __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7]));
+            } else if (vec) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {

@@ -83,6 +83,17 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* v) {
                :
                : "memory");
 }
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per instruction -- the thread-per-row epilogues would
+// otherwise write every sector in two 16-byte halves
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
+                                              uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 // named barrier among the four epilogue warps (barrier 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
