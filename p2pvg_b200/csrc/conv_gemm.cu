@@ -196,6 +196,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t da0 = A_MN ? make_desc(smem0, 64 * 128, 1024) : make_desc(smem0, 0, 1024);
+      const uint64_t db0 = B_MN ? make_desc(smem0 + A_STAGE_BYTES, 64 * 128, 1024) : make_desc(smem0 + A_STAGE_BYTES, 0, 1024);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
         int z = 0;
@@ -214,12 +217,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t par = (it / C_::STAGES) & 1;
           mbar_wait(&full_bar[s], par);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          // descriptors of stage 0 / k 0 are built once; the start-address field (bits 0-13, address >> 4) is advanced by
+          // plain additions -- the single issuing thread has ~32 clk per 128x64x16 MMA to spend
+          const uint64_t stage_off = (uint64_t)((uint32_t)s * (uint32_t)(C_::STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; k++) {
-            const uint64_t da = A_MN ? make_desc(sa + k * UMMA_K * 128, 64 * 128, 1024) : make_desc(sa + k * 32, 0, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * UMMA_K * 128, 64 * 128, 1024) : make_desc(sb + k * 32, 0, 1024);
+            const uint64_t da = da0 + stage_off + (uint64_t)(k * ((A_MN ? UMMA_K * 128 : 32) >> 4));
+            const uint64_t db = db0 + stage_off + (uint64_t)(k * ((B_MN ? UMMA_K * 128 : 32) >> 4));
             umma_bf16(tmem_c, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);

@@ -227,6 +227,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t fmt = TF32 ? 2u : 1u;  // 1 = bf16, 2 = tf32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t da0 = A_MN ? make_desc(smem0, BLOCK_K * 128, 1024) : make_desc(smem0, 0, 1024);
+      const uint64_t db0 = B_MN ? make_desc(smem0 + A_STAGE_BYTES, BLOCK_K * 128, 1024) : make_desc(smem0 + A_STAGE_BYTES, 0, 1024);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
         const int z = (splits == 1) ? 0 : t / tiles_mn;
