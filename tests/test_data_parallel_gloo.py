@@ -24,13 +24,13 @@ def shard(rank):
     return x, eps
 
 
-def worker(rank, port, out):
+def worker(rank, port, out, mode="B"):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     state = O.build_state(CFG64, seed=1)
     opt = O.default_opt(batch_size=B_LOCAL)
-    eng = TrainEngine(state, CFG64, opt, EmuKernels("cpu"), mode="B")
+    eng = TrainEngine(state, CFG64, opt, EmuKernels("cpu"), mode=mode)
     eng.dist = (dist, None, WORLD)
     x, eps = shard(rank)
     probs = np.random.RandomState(0).uniform(0, 1, T - 1)  # identical skip mask on every rank
@@ -77,3 +77,20 @@ def test_two_replicas_average_gradients(tmp_path):
             assert dw.max().item() <= 2.2e-3, f"{m}.{k}"
             if solid.any():
                 assert dw[solid].max().item() <= 2e-5 + 1e-4, f"{m}.{k}: {dw[solid].max().item():.3e}"
+
+
+def test_two_replicas_mode_a_stay_identical():
+    """Mode A (the reference's two-phase update) needs two exchange points per step -- the four non-prior arenas after
+    backward #1 and the prior arena after backward #2; both must be averaged or the replicas drift apart."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = mp.Manager().dict()
+    mp.spawn(worker, args=(port, out, "A"), nprocs=WORLD, join=True)
+    assert out["same"], "replicas diverged in Mode A"
+    assert np.all(np.isfinite(out["losses"]))
+    # the prior moved (its gradients were exchanged and applied), and by no more than one Adam step
+    st = O.build_state(CFG64, seed=1)
+    dw = max((out["params"]["prior"][k] - st["prior"][k]).abs().max().item() for k in st["prior"] if O.is_param(k))
+    assert 0 < dw <= 2.2e-3
