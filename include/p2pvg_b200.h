@@ -44,19 +44,27 @@ const char* p2pvg_last_error(void);
 int p2pvg_has_tcgen05(void);
 /* 0 = pick automatically (tcgen05 for bf16 operands), 1 = force the CUDA-core GEMM, 2 = force tcgen05 */
 int p2pvg_set_gemm_impl(int impl);
-/* fp32-operand GEMMs: 0 = exact fp32 on the CUDA cores (parity mode), 1 = tcgen05 kind::tf32 when both operands are
- * K-major and TMA-compatible (used for the LSTM GEMMs of the bf16 training mode). */
-int p2pvg_set_fp32_gemm_mode(int mode);
+/* p2pvg_gemm `flags` (per call; there is no process-global precision state):
+ *   P2PVG_GEMM_TF32          fp32 operands MAY run on tcgen05 kind::tf32 (LSTM GEMMs of the bf16 training mode).  The
+ *                            tensor-core kernel needs both operands K-major, K >= 32, 16-byte aligned bases and row
+ *                            pitches (TMA); any other fp32 GEMM of such a call runs on the exact CUDA-core kernel --
+ *                            a documented, precision-INCREASING dispatch between two kernels of this library (never a
+ *                            CPU or vendor-library fallback).
+ *   P2PVG_GEMM_TF32_REQUIRE  with P2PVG_GEMM_TF32: return P2PVG_ERR_UNSUPPORTED instead of dispatching to the
+ *                            CUDA-core kernel when the operands are not TMA-compatible. */
+#define P2PVG_GEMM_TF32 1
+#define P2PVG_GEMM_TF32_REQUIRE 2
 
 /* C[M,N] = (accumulate ? C : 0) + opA(A)*opB(B) + bias[n] + addend[m,n]
  *   a_mn=0: A[m*lda+k] (K-major), a_mn=1: A[k*lda+m];  b_mn=0: B[n*ldb+k], b_mn=1: B[k*ldb+n].
  * Replaces the library GEMMs behind nn.Conv2d / nn.ConvTranspose2d (models/dcgan_64.py:8,20,43,64,76 after
  * lowering), nn.Linear and nn.LSTMCell (models/lstm.py:13-17,54-57) and their autograd backward.
- * bf16 operands run on tcgen05 tensor cores (fp32 accumulation in TMEM); fp32 operands on CUDA cores.
+ * bf16 operands run on tcgen05 tensor cores (fp32 accumulation in TMEM); fp32 operands on CUDA cores (exact) unless
+ * `flags` allows TF32 (see above).
  * workspace: split-K partials for the tensor-core path (may be NULL when ws_bytes == 0). */
 int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int c_dtype,
                int64_t ldc, int M, int N, int K, int accumulate, const float* bias, const void* addend, int64_t ldd,
-               void* workspace, size_t ws_bytes, void* stream);
+               void* workspace, size_t ws_bytes, int flags, void* stream);
 
 /* Implicit-GEMM 4x4 / stride-2 / pad-1 convolution family on NHWC bf16 tensors (TMA 4-D pixel-box loads feeding tcgen05;
  * no im2col / col2im buffers).  H, W = size of the SMALL map (the big map is 2H x 2W).

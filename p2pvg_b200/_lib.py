@@ -58,8 +58,30 @@ def _p(t):
     return _vp(t.data_ptr())
 
 
+class _Workspaces:
+    """Scratch buffers of one device, shared by every CudaKernels view of it.  ``gen`` counts re-allocations: a captured
+    CUDA graph that used a workspace is stale once it moved (TrainEngine.graph_generation)."""
+
+    def __init__(self):
+        self.gemm, self.bn, self.gen = {}, {}, 0
+
+
+_BACKENDS = {}
+
+
+def kernels_for(device):
+    """The one kernel backend of a device (workspaces are allocated once per device, not per caller)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("p2pvg_b200 has no CPU path: CUDA tensors / modules only")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _BACKENDS:
+        _BACKENDS[idx] = CudaKernels(torch.device("cuda", idx))
+    return _BACKENDS[idx]
+
+
 class CudaKernels:
-    """Launches the sm_100a kernels on the current torch CUDA stream."""
+    """Launches the sm_100a kernels on the current torch CUDA stream of its device."""
 
     name = "cuda"
 
@@ -68,14 +90,29 @@ class CudaKernels:
         if not torch.cuda.is_available():
             raise RuntimeError("p2pvg_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda")
-        self._gemm_ws = {}
-        self._bn_ws = {}
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._ws = _Workspaces()
         self.lane = 0   # workspace set in use: the engine switches to lane 1 for work enqueued on its side stream
         self.launches = 0
+        self.gemm_flags = 0   # P2PVG_GEMM_* flags passed with every p2pvg_gemm call of this view
+
+    def with_mode(self, tf32: bool):
+        """A view of this backend (same library, same workspaces) whose fp32-operand GEMMs may (tf32=True) or may not run
+        at TF32 precision.  The precision policy travels with every call; nothing is process-global."""
+        import copy
+        v = copy.copy(self)
+        v.gemm_flags = 1 if tf32 else 0
+        v.launches = 0
+        return v
+
+    @property
+    def ws_gen(self):
+        return self._ws.gen
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self):
-        return _vp(torch.cuda.current_stream().cuda_stream)
+        return _vp(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _ck(self, rc):
         self.launches += 1
@@ -83,16 +120,18 @@ class CudaKernels:
             raise KernelError(f"p2pvg_b200 error {rc}: {self.lib.p2pvg_last_error().decode()}")
 
     def gemm_workspace(self):
-        ws = self._gemm_ws.get(self.lane)
+        ws = self._ws.gemm.get(self.lane)
         if ws is None:
-            ws = self._gemm_ws[self.lane] = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+            ws = self._ws.gemm[self.lane] = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+            self._ws.gen += 1
         return ws
 
     def bn_workspace(self, G, C):
         need = self.lib.p2pvg_bn_workspace_bytes(_i(G), _i(C))
-        ws = self._bn_ws.get(self.lane)
+        ws = self._ws.bn.get(self.lane)
         if ws is None or ws.numel() < need:
-            ws = self._bn_ws[self.lane] = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=self.device)
+            ws = self._ws.bn[self.lane] = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=self.device)
+            self._ws.gen += 1
         return ws
 
     def set_gemm_impl(self, impl: str):
@@ -100,10 +139,9 @@ class CudaKernels:
         self.launches -= 1
 
     def set_fp32_gemm_mode(self, mode: int):
-        """0: fp32 GEMMs exact on the CUDA cores; 1: K-major fp32 GEMMs on the tensor cores at TF32 precision."""
-        rc = self.lib.p2pvg_set_fp32_gemm_mode(_i(mode))
-        if rc != 0:
-            raise KernelError("set_fp32_gemm_mode failed")
+        """0: fp32 GEMMs exact on the CUDA cores; 1: K-major fp32 GEMMs on the tensor cores at TF32 precision
+        (this view only; passed per call as P2PVG_GEMM_TF32)."""
+        self.gemm_flags = 1 if mode else 0
 
     def has_tcgen05(self) -> bool:
         return bool(self.lib.p2pvg_has_tcgen05())
@@ -119,7 +157,7 @@ class CudaKernels:
         ws = self.gemm_workspace()
         self._ck(self.lib.p2pvg_gemm(_p(A), _i(_dt(A)), _i(int(a_mn)), _i64(lda), _p(B), _i(int(b_mn)), _i64(ldb), _p(C),
                                      _i(_dt(C)), _i64(ldc), _i(M), _i(N), _i(K), _i(int(accumulate)), _p(bias), _p(addend),
-                                     _i64(ldd), _p(ws), _sz(ws.numel() if ws is not None else 0), self._stream()))
+                                     _i64(ldd), _p(ws), _sz(ws.numel() if ws is not None else 0), _i(self.gemm_flags), self._stream()))
 
     # -- implicit-GEMM convolutions ---------------------------------------------------------
     def conv_gemm(self, kind, a, b, c, N, H, W, Ck, Cn, Cm=0, ldb=None, ldc=None, bias=None, addend=None, grp_src=None,

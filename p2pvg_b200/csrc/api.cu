@@ -94,7 +94,6 @@ int p2pvg_scale_impl(float*, long long, float, cudaStream_t);
 
 static int g_gemm_impl = 0;  // 0 auto, 1 simt, 2 tcgen05
 int p2pvg_gemm_impl_forced() { return g_gemm_impl; }
-static int g_fp32_mode = 0;  // 0 exact fp32 on CUDA cores, 1 TF32 tensor cores for K-major fp32 operands
 
 #define ST ((cudaStream_t)stream)
 
@@ -109,15 +108,9 @@ int p2pvg_set_gemm_impl(int impl) {
   return P2PVG_OK;
 }
 
-int p2pvg_set_fp32_gemm_mode(int mode) {
-  if (mode < 0 || mode > 1) return P2PVG_ERR_BAD_ARG;
-  g_fp32_mode = mode;
-  return P2PVG_OK;
-}
-
 int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int c_dtype,
                int64_t ldc, int M, int N, int K, int accumulate, const float* bias, const void* addend, int64_t ldd,
-               void* workspace, size_t ws_bytes, void* stream) {
+               void* workspace, size_t ws_bytes, int flags, void* stream) {
   P2PVG_REQUIRE(A && B && C, P2PVG_ERR_BAD_ARG, "gemm: null operand");
   P2PVG_REQUIRE(M >= 0 && N >= 0 && K >= 0, P2PVG_ERR_BAD_ARG, "gemm: negative size");
   bool want_tc = (in_dtype == P2PVG_BF16) && g_gemm_impl != 1;
@@ -125,9 +118,17 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
   // refuse to fall back when an operand is not TMA-compatible.
   if (want_tc)
     return p2pvg_gemm_tc(A, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace, ws_bytes, ST);
-  if (in_dtype == P2PVG_F32 && g_fp32_mode == 1 && g_gemm_impl != 1 && !a_mn && !b_mn && K >= 32) {
-    int rc = p2pvg_gemm_tf32(A, lda, B, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, ST);
-    if (rc != P2PVG_ERR_UNSUPPORTED) return rc;  // not TMA-compatible -> CUDA-core kernel below
+  if (in_dtype == P2PVG_F32 && (flags & P2PVG_GEMM_TF32) && g_gemm_impl != 1) {
+    // documented dispatch (include/p2pvg_b200.h): TF32 tensor cores for K-major TMA-compatible operands, the exact
+    // CUDA-core kernel otherwise -- unless the caller asked for an error instead
+    int rc = P2PVG_ERR_UNSUPPORTED;
+    if (!a_mn && !b_mn && K >= 32) rc = p2pvg_gemm_tf32(A, lda, B, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, ST);
+    if (rc != P2PVG_ERR_UNSUPPORTED) return rc;
+    if (flags & P2PVG_GEMM_TF32_REQUIRE) {
+      p2pvg_set_error("gemm: fp32 operands not eligible for the TF32 tensor-core kernel (need K-major, K >= 32, 16-byte aligned bases / pitches): M=%d N=%d K=%d a_mn=%d b_mn=%d",
+                      M, N, K, a_mn, b_mn);
+      return P2PVG_ERR_UNSUPPORTED;
+    }
   }
   return p2pvg_gemm_simt(A, in_dtype, a_mn, lda, B, b_mn, ldb, C, c_dtype, ldc, M, N, K, accumulate, bias, addend, ldd, workspace,
                          ws_bytes, ST);

@@ -13,6 +13,11 @@ from __future__ import annotations
 import torch
 
 
+def _chain_front(first, rest):
+    yield first
+    yield from rest
+
+
 class DevicePrefetcher:
     def __init__(self, batches, device, depth: int = 2):
         self.it = iter(batches)
@@ -24,8 +29,10 @@ class DevicePrefetcher:
         self.slots = [None] * self.depth      # device buffers, reused round-robin
         self.free_ev = [None] * self.depth    # compute-stream event: the slot's previous consumer has been enqueued
         self.pinned = [None] * self.depth
+        self.copied_ev = [None] * self.depth  # copy-stream event: the slot's last H2D copy (reads the pinned staging buffer)
         self.n = 0
         self.queue = []
+        self._pending_release = None
         self._fill()
 
     def _issue(self):
@@ -34,8 +41,13 @@ class DevicePrefetcher:
         except StopIteration:
             return False
         k = self.n % self.depth
+        if k == self._pending_release:
+            self.it = _chain_front(host, self.it)   # slot still in use by the un-released batch: retry later
+            return False
         self.n += 1
         if not host.is_pinned():  # page-locked staging buffer (reused); pinned inputs are copied from directly
+            if self.copied_ev[k] is not None:
+                self.copied_ev[k].synchronize()   # the previous copy out of this staging buffer must have finished
             if self.pinned[k] is None or self.pinned[k].shape != host.shape or self.pinned[k].dtype != host.dtype:
                 self.pinned[k] = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
             self.pinned[k].copy_(host)
@@ -48,6 +60,7 @@ class DevicePrefetcher:
             self.slots[k].copy_(host, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
+        self.copied_ev[k] = ready
         self.queue.append((k, ready))
         return True
 
@@ -59,23 +72,31 @@ class DevicePrefetcher:
         return self
 
     def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        # everything the caller enqueued since the previous batch was handed out has consumed it: mark its slot
+        # re-usable now (an explicit release() after the step does the same earlier)
+        self.release()
         if not self.queue:
             self._fill()
             if not self.queue:
                 raise StopIteration
         k, ready = self.queue.pop(0)
-        cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ready)
         x = self.slots[k]
-        ev = torch.cuda.Event()
-        self.free_ev[k] = ev
+        # until released, the slot must not be refilled: an un-recorded event would not block the copy stream, so
+        # the slot is simply not re-issued before release (depth >= 2 keeps one batch in flight meanwhile)
+        self.free_ev[k] = None
+        self._pending_release = k
         self._fill()          # start copying the next batch before the caller blocks on this step's results
-        # the caller enqueues its work after this returns; `release` marks the point after which slot k may be refilled
-        self._pending_release = (k, ev)
         return x
 
     def release(self):
-        """Record that everything enqueued so far has consumed the last batch (call after the step; optional when the
-        consumer copies the batch into its own static buffer first, as the CUDA-graph step does)."""
-        k, ev = self._pending_release
+        """Record that everything enqueued so far on the compute stream has consumed the last batch.  Called
+        automatically when the next batch is requested; calling it right after the step lets the refill start earlier."""
+        if self._pending_release is None:
+            return
+        k, self._pending_release = self._pending_release, None
+        ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
+        self.free_ev[k] = ev
+        self._fill()

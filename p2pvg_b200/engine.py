@@ -122,7 +122,10 @@ def is_param_key(key):
 class TrainEngine:
     def __init__(self, state, cfg, opt, kernels, act_dtype=torch.float32, mode="A"):
         """state: module -> {state_dict key: tensor} (reference key names)."""
-        self.K = kernels
+        # bf16 mode: the fp32 LSTM GEMMs run on the tensor cores at TF32 precision; fp32 mode stays exact.  The policy is
+        # a property of this engine's view of the backend and travels with every GEMM call.
+        tc_lstm = (act_dtype == torch.bfloat16) and hasattr(kernels, "with_mode")
+        self.K = kernels.with_mode(tc_lstm) if hasattr(kernels, "with_mode") else kernels
         self.dev = kernels.device
         self.cfg, self.opt = dict(cfg), dict(opt)
         self.adt = act_dtype
@@ -146,11 +149,11 @@ class TrainEngine:
             self.arena[m] = ParamArena(params, self.dev)
             self.buffers[m] = {k: v.detach().clone().to(self.dev) for k, v in state[m].items() if not is_param_key(k)}
         self._bufs = {}
+        self._buf_gen = 0
         self._packed = {}
         self._graphs = {}
         self.dist = None  # (torch.distributed, group, world_size) when batch-sharded over several GPUs
-        # bf16 mode: the fp32 LSTM GEMMs run on the tensor cores at TF32 precision; fp32 mode stays exact
-        self.tc_lstm = (act_dtype == torch.bfloat16) and hasattr(kernels, "set_fp32_gemm_mode")
+        self.tc_lstm = tc_lstm
         # bf16 mode: 4x4/s2 (transposed) convolutions with >= 64 channels on both sides run as implicit GEMMs (4-D TMA
         # pixel-box gathers), without im2col / col2im buffers; P2PVG_IMPLICIT=0 keeps the explicit lowering
         import os
@@ -201,7 +204,7 @@ class TrainEngine:
         if self._side_dirty:
             ev = torch.cuda.Event()
             ev.record(self.side)
-            torch.cuda.current_stream().wait_event(ev)
+            torch.cuda.current_stream(self.dev).wait_event(ev)
             self._side_dirty = False
 
     # ------------------------------------------------------------------ memory
@@ -209,9 +212,18 @@ class TrainEngine:
         dtype = dtype or self.adt
         t = self._bufs.get(name)
         if t is None or t.numel() < numel or t.dtype != dtype:
+            if t is not None:
+                # a captured CUDA graph holds the raw address of every buffer it touched: once one of them is
+                # re-allocated (a longer sequence, more executed steps) every graph captured so far is stale
+                self._buf_gen += 1
             t = torch.zeros(int(numel), dtype=dtype, device=self.dev)
             self._bufs[name] = t
         return t
+
+    def graph_generation(self):
+        """Changes whenever a buffer a captured graph may have baked in was re-allocated (engine pool or the
+        kernel backend's workspaces)."""
+        return (self._buf_gen, getattr(self.K, "ws_gen", 0))
 
     def fbuf(self, name, numel):
         return self.buf(name, numel, torch.float32)
@@ -354,23 +366,38 @@ class TrainEngine:
         """CUDA-graph replay of the whole step.  The first call with a new (T,B,S,...) signature runs eagerly
         (allocating every buffer), the second captures, later ones only replay; index tables, counters and
         inputs live in static device buffers that are refreshed before each replay."""
-        key = plan.key + (self.B,)
+        # host scalars that the kernels receive by value are part of the signature: a replay would silently keep
+        # the values seen at capture time (lr, loss weights, configured batch size, Adam beta1)
+        opt = self.opt
+        key = plan.key + (self.B, tuple(x.shape[2:]), float(opt["lr"]), float(opt["beta1"]), float(opt["beta"]),
+                          float(opt["weight_align"]), float(opt["weight_cpc"]), int(opt["batch_size"]), self.mode,
+                          self.dist[2] if self.dist is not None else 1)
         xs = self.fbuf("x_static", x.numel()).view(-1)[:x.numel()].view(x.shape)
         es = self.fbuf("eps_static", eps.numel()).view(-1)[:eps.numel()].view(eps.shape)
         xs.copy_(x, non_blocking=True)
         es.copy_(eps, non_blocking=True)
         self.eps = es
         st = self._graphs.get(key)
+        if st is not None and st != "warm" and st[2] != self.graph_generation():
+            st = None   # some buffer moved since this graph was captured
         if st is None:
+            # eager run: allocates / grows every buffer this signature needs
+            gen0 = self.graph_generation()
+            out = self._run(xs, plan)
+            if self.graph_generation() != gen0:
+                self._graphs.clear()   # older graphs point into freed buffers
             self._graphs[key] = "warm"
-            return self._run(xs, plan)
+            return out
         if st == "warm":
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = self.K.launches
+            gen0 = self.graph_generation()
             with torch.cuda.graph(g):
                 self._run(xs, plan)
-            self._graphs[key] = st = (g, self.K.launches - n0)
+            if self.graph_generation() != gen0:
+                raise RuntimeError("a buffer was re-allocated during CUDA-graph capture (the warm-up run must size every buffer)")
+            self._graphs[key] = st = (g, self.K.launches - n0, gen0)
         st[0].replay()
         self.K.launches += st[1]
         return self._bufs["loss_out"][:4]
@@ -389,8 +416,6 @@ class TrainEngine:
 
     def _run_inner(self, x, plan):
         self._mark("start")
-        if hasattr(self.K, "set_fp32_gemm_mode"):
-            self.K.set_fp32_gemm_mode(1 if self.tc_lstm else 0)
         self.pack_weights()
         self.pack_lstm_weights()
         self._mark("pack")

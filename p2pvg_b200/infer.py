@@ -13,17 +13,17 @@ import torch
 
 from ._lib import ACT_LRELU, ACT_NONE, ACT_SIGMOID, ACT_TANH, CudaKernels
 
-_KERNELS = {}
+_EXACT = {}
 
 
 def kernels_for(device):
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise RuntimeError("p2pvg_b200 has no CPU path: tensors must live on a CUDA device")
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    if key not in _KERNELS:
-        _KERNELS[key] = CudaKernels(torch.device("cuda", key))
-    return _KERNELS[key]
+    """Exact-fp32-GEMM view of the device's one kernel backend (fp32 operands only occur in parity mode on the
+    stand-alone module forwards: keep them exact)."""
+    from ._lib import kernels_for as backend_for
+    base = backend_for(device)
+    if base.device.index not in _EXACT:
+        _EXACT[base.device.index] = base.with_mode(False)
+    return _EXACT[base.device.index]
 
 
 def _act_dtype():
@@ -55,7 +55,6 @@ def _stages(mod):
 def encoder_forward(mod, x):
     K = kernels_for(x.device)
     dev, adt = x.device, _act_dtype()
-    K.set_fp32_gemm_mode(0)  # fp32 operands only occur in parity mode here: keep them exact
     chans = _stages(mod)
     n = len(chans)
     B, nc, H = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
@@ -109,7 +108,6 @@ def _to_nhwc(K, t, adt):
 def decoder_forward(mod, vec, skip):
     K = kernels_for(vec.device)
     dev, adt = vec.device, _act_dtype()
-    K.set_fp32_gemm_mode(0)
     chans = _stages(mod)
     n, g = len(chans), mod.dim
     vec = vec.reshape(-1, g).float().contiguous()
@@ -164,7 +162,6 @@ def _lstm_cells(K, mod, inp):
     x = inp.reshape(-1, mod.input_size).float().contiguous()
     B = int(x.shape[0])
     h_in = torch.empty(B, R, device=dev)
-    K.set_fp32_gemm_mode(0)
     K.gemm(x, mod.embed.weight.data, h_in, B, R, mod.input_size, bias=mod.embed.bias.data)
     for l, cell in enumerate(mod.lstm):
         h_prev, c_prev = mod.hidden[l]
@@ -285,7 +282,6 @@ def _residual_linear(K, rl, x, rows):
 @torch.no_grad()
 def mlp_encoder_forward(mod, x):
     K = kernels_for(x.device)
-    K.set_fp32_gemm_mode(0)
     B = int(x.shape[0])
     xf = x.reshape(B, -1).float().contiguous()
     h1 = _residual_linear(K, mod.fc1, xf, B)
@@ -296,7 +292,6 @@ def mlp_encoder_forward(mod, x):
 @torch.no_grad()
 def mlp_decoder_forward(mod, vec, skip):
     K = kernels_for(vec.device)
-    K.set_fp32_gemm_mode(0)
     vec = vec.float().contiguous()
     B = int(vec.shape[0])
     d1 = _residual_linear(K, mod.fc1, vec, B)

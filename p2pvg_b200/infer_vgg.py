@@ -51,7 +51,6 @@ def _layer(K, blk, a, N, H, adt, dev, extra=None):
 def vgg_encoder_forward(mod, x):
     K = kernels_for(x.device)
     dev, adt = x.device, _act_dtype()
-    K.set_fp32_gemm_mode(0)
     B, nc, H = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
     if H != mod.image_width or int(x.shape[3]) != mod.image_width:
         raise ValueError(f"this vgg backbone expects {mod.image_width}x{mod.image_width} frames")
@@ -90,7 +89,6 @@ def vgg_encoder_forward(mod, x):
 def vgg_decoder_forward(mod, vec, skip):
     K = kernels_for(vec.device)
     dev, adt = vec.device, _act_dtype()
-    K.set_fp32_gemm_mode(0)
     g, nc = mod.dim, mod.nc
     vec = vec.reshape(-1, g).float().contiguous()
     B = int(vec.shape[0])

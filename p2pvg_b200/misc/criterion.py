@@ -11,10 +11,10 @@ class KLCriterion(nn.Module):
 
     def forward(self, mu1, logvar1, mu2, logvar2):
         """KL(N(mu1, e^logvar1) || N(mu2, e^logvar2)) summed, divided by the *configured* opt.batch_size."""
-        from .._lib import CudaKernels
+        from .._lib import kernels_for
         if not mu1.is_cuda:
             raise RuntimeError("p2pvg_b200 has no CPU path: KLCriterion needs CUDA tensors")
-        K = CudaKernels(mu1.device)
+        K = kernels_for(mu1.device)   # the device's one backend (no per-call workspace allocation)
         n = mu1.numel()
         args = [t.detach().contiguous().float() for t in (mu1, logvar1, mu2, logvar2)]
         zeros = torch.zeros(n, device=mu1.device)

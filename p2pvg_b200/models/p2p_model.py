@@ -26,7 +26,11 @@ class ArenaAdam(torch.optim.Optimizer):
     engine inside the train step (PyTorch-1.0 arithmetic, which is what the reference pins)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
-        super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps))
+        # the param_groups carry every key stock torch.optim.Adam reads in step(), so that a checkpoint written here
+        # resumes under the reference's real optim.Adam (Adam.load_state_dict replaces its param_groups with the saved ones)
+        super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                                            foreach=None, capturable=False, differentiable=False, fused=None,
+                                            decoupled_weight_decay=False))
         self._arena = None
         self._names = None
 
@@ -130,7 +134,7 @@ class P2PModel(nn.Module):
     def engine(self, width):
         if self._engine is not None:
             return self._engine
-        from .._lib import CudaKernels
+        from .._lib import kernels_for
         from ..engine import TrainEngine
         from ..engine_mlp import TrainEngineMLP
         from ..engine_vgg import TrainEngineVGG
@@ -142,7 +146,7 @@ class P2PModel(nn.Module):
         state = {m: getattr(self, m).state_dict() for m in MODULES}
         adt = torch.float32 if self.precision == "fp32" else torch.bfloat16
         cls = {"mlp": TrainEngineMLP, "vgg": TrainEngineVGG}.get(cfg["backbone"], TrainEngine)
-        eng = cls(state, cfg, self._opt_dict(), CudaKernels(dev), act_dtype=adt, mode=self.update_mode)
+        eng = cls(state, cfg, self._opt_dict(), kernels_for(dev), act_dtype=adt, mode=self.update_mode)
         for m in MODULES:
             mod = getattr(self, m)
             named = list(mod.named_parameters())

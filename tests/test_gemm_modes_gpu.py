@@ -1,5 +1,5 @@
 """TF32 tensor-core path for fp32 operands and split-K of the CUDA-core GEMM (C ABI: p2pvg_gemm with
-p2pvg_set_fp32_gemm_mode), against the torch emulation."""
+flags = P2PVG_GEMM_TF32), against the torch emulation."""
 import pytest
 import torch
 

@@ -1,0 +1,223 @@
+"""Parity of the CUDA train step AT THE CONFIGURATIONS THE BENCH MEASURES: the bf16 tensor-core
+mode, CUDA-graph replay, cluster LSTM scans, 128x256 tiles and the split-K cost model at the sequence length of
+BASELINE's configs — against the CPU oracle (reference models/p2p_model.py:185-271, Mode A).
+
+Stated tolerances of the measured (bf16 operands / fp32 accumulate, TF32 LSTM GEMMs) mode:
+  * the four losses: rtol 1e-2;
+  * every gradient tensor: cosine >= 0.995 (dcgan_64, h36m_mlp), >= 0.99 (vgg_64), norm ratio within 5 %;
+  * post-step weights: elements whose oracle gradient is solid (|g| > 3 % of the tensor's max) moved by the same Adam
+    step as the oracle's to 1.2e-4 (lr = 1e-3: an engine that skipped Adam, or stepped the wrong way, is off by 1e-3 /
+    2e-3); every element within 2.2 lr;
+  * skip / time-counter logic: bit-exact (host side, tests/test_oracle_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import p2p_oracle as O
+from p2pvg_b200.engine import StepPlan, TrainEngine
+from tests.test_engine_emu import CFG64, bn_cancelled_bias
+
+pytestmark = pytest.mark.gpu
+LR = 1e-3
+
+
+def snapshot(eng):
+    return {m: (eng.arena[m].flat.clone(), {k: v.clone() for k, v in eng.buffers[m].items()}) for m in O.MODULES}
+
+
+def restore(eng, snap):
+    """Back to the initial state IN PLACE (captured graphs keep pointing at the same arenas)."""
+    for m in O.MODULES:
+        A = eng.arena[m]
+        A.flat.copy_(snap[m][0])
+        A.grad.zero_()
+        A.m.zero_()
+        A.v.zero_()
+        A.step_t.zero_()
+        for k, v in snap[m][1].items():
+            eng.buffers[m][k].copy_(v)
+
+
+def check_step(ref, state_after, got, eng, rtol_loss, min_cos, what, cancelled=bn_cancelled_bias, min_cos_median=None):
+    np.testing.assert_allclose(got, np.array(ref["losses"], dtype=np.float32), rtol=rtol_loss, atol=1e-6, err_msg=what)
+    coss = []
+    for m in O.MODULES:
+        gmax = max(g.abs().max().item() for g in ref["grads"][m].values())
+        for k, gref in ref["grads"][m].items():
+            g = eng.arena[m].g[k].detach().float().cpu()
+            w = eng.arena[m].p[k].detach().cpu()
+            dw = (w - state_after[m][k]).abs()
+            assert dw.max().item() <= 2.2 * LR, f"{what} weight {m}.{k}: moved {dw.max().item():.3e}"
+            if cancelled(m, k):
+                assert g.abs().max().item() <= 3e-2 * gmax, f"{what} grad {m}.{k} should be ~0"
+                continue
+            cos = torch.nn.functional.cosine_similarity(g.flatten().double(), gref.flatten().double(), dim=0).item()
+            coss.append((cos, f"{m}.{k}"))
+            assert cos >= min_cos, f"{what} grad {m}.{k}: cosine {cos:.6f}"
+            r = g.norm().item() / (gref.norm().item() + 1e-30)
+            assert abs(r - 1) < 0.05, f"{what} grad {m}.{k}: norm ratio {r:.5f}"
+            solid = gref.abs() > 3e-2 * (gref.abs().max() + 1e-30)
+            # a solid element whose bf16 gradient still has the oracle's sign takes the oracle's Adam step
+            agree = solid & (torch.sign(g) == torch.sign(gref))
+            assert agree.sum().item() >= 0.999 * solid.sum().item(), f"{what} grad {m}.{k}: sign flips on solid elements"
+            if agree.any():
+                assert dw[agree].max().item() <= 1.2e-4, f"{what} weight {m}.{k}: {dw[agree].max().item():.3e} on solid elements"
+    if min_cos_median is not None:
+        assert float(np.median([c for c, _ in coss])) >= min_cos_median, sorted(coss)[:5]
+    return sorted(coss)[:3]
+
+
+def dcgan_case(T, B, optkw, np_seed):
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    cfg = CFG64
+    state = O.build_state(cfg, seed=1)
+    opt = O.default_opt(**optkw)
+    opt["batch_size"] = opt["batch_size"] or B
+    x = torch.rand(T, B, 1, 64, 64, generator=torch.Generator().manual_seed(5))
+    probs = np.random.RandomState(np_seed).uniform(0, 1, T - 1)
+    eps = O.draw_eps(StepPlan(T, probs, opt).S, B, cfg["z_dim"], seed=11)
+    return cfg, state, opt, x, probs, eps
+
+
+@pytest.mark.parametrize("optkw,np_seed", [({}, 0), (dict(skip_prob=0.5), 0)], ids=["skip0", "skip0.5"])
+def test_c1_shape_bf16_graph_cluster_vs_oracle(optkw, np_seed):
+    """BASELINE configs[0] shape (T=30, B=16, dcgan_64) in the benched mode: bf16 + CUDA graph + cluster scans."""
+    from p2pvg_b200._lib import kernels_for
+    T, B = 30, 16
+    cfg, state, opt, x, probs, eps = dcgan_case(T, B, optkw, np_seed)
+    eng = TrainEngine(O.clone_state(state), cfg, opt, kernels_for("cuda"), act_dtype=torch.bfloat16)
+    assert eng.implicit and eng.fused_scan and eng.tc_lstm
+    snap = snapshot(eng)
+    xd, ed = x.cuda(), eps.cuda()
+    # eager (allocates), capture + first replay, replay: the compared result is a pure graph REPLAY from the initial state
+    # with frame skipping the graph is captured on ANOTHER skip pattern of the same (T, S, ...) signature: the replay
+    # only sees new index tables / time counters
+    other, key = probs, StepPlan(T, probs, opt).key
+    for sd in range(100, 400):
+        cand = np.random.RandomState(sd).uniform(0, 1, T - 1)
+        pc = StepPlan(T, cand, opt)
+        if optkw and pc.key == key and pc.tgt_frame != StepPlan(T, probs, opt).tgt_frame:
+            other = cand
+            break
+    assert not optkw or other is not probs, "no second skip pattern with the same signature found"
+    for _ in range(2):
+        e2 = O.draw_eps(StepPlan(T, other, opt).S, B, cfg["z_dim"], seed=3).cuda()
+        eng.step(xd, probs=other, eps=e2, use_graph=True)
+    restore(eng, snap)
+    got = eng.step(xd, probs=probs, eps=ed, use_graph=True)
+    assert any(v != "warm" for v in eng._graphs.values()), "the step was not graph-replayed"
+    adam = {m: O.new_adam_state(state[m]) for m in O.MODULES}
+    ref = O.train_step(state, adam, x, opt, 64, eps, probs, mode="A")
+    worst = check_step(ref, state, got, eng, 1e-2, 0.995, f"C1/{optkw}")
+    print("worst cosines", worst)
+
+
+def test_graph_survives_growing_sequences():
+    """graphs captured for a short sequence must not be replayed after the buffer pool grew for a
+    longer one.  small -> large -> small with graphs on equals eager from the same state."""
+    from p2pvg_b200._lib import kernels_for
+    B = 4
+    cfg = CFG64
+    state = O.build_state(cfg, seed=1)
+    opt = O.default_opt(batch_size=B)
+    engs = [TrainEngine(O.clone_state(state), cfg, opt, kernels_for("cuda"), act_dtype=torch.bfloat16) for _ in range(2)]
+    gen = torch.Generator().manual_seed(3)
+    seq = [4, 4, 4, 9, 9, 9, 4, 6, 4, 9]
+    for it, T in enumerate(seq):
+        x = torch.rand(T, B, 1, 64, 64, generator=gen).cuda()
+        probs = np.random.RandomState(it).uniform(0, 1, T - 1)
+        eps = O.draw_eps(T - 1, B, 10, seed=it).cuda()
+        a = engs[0].step(x, probs=probs, eps=eps, use_graph=True)
+        b = engs[1].step(x, probs=probs, eps=eps, use_graph=False)
+        np.testing.assert_allclose(a, b, rtol=2e-3, atol=1e-6, err_msg=f"iteration {it} (T={T})")
+    for m in O.MODULES:
+        d = (engs[0].arena[m].flat - engs[1].arena[m].flat).abs().max().item()
+        assert d <= 2.5e-3, f"{m}: graph / eager weights diverged by {d}"
+
+
+def test_graph_key_tracks_host_scalars():
+    """lr / loss weights are kernel arguments baked into a captured graph — a change must re-capture."""
+    from p2pvg_b200._lib import kernels_for
+    T, B = 4, 4
+    cfg, state, opt, x, probs, eps = dcgan_case(T, B, {}, 0)
+    eng = TrainEngine(O.clone_state(state), cfg, opt, kernels_for("cuda"), act_dtype=torch.bfloat16)
+    snap = snapshot(eng)
+    for _ in range(3):
+        eng.step(x.cuda(), probs=probs, eps=eps.cuda(), use_graph=True)
+    restore(eng, snap)
+    eng.opt = dict(eng.opt, lr=0.0)
+    for _ in range(3):
+        eng.step(x.cuda(), probs=probs, eps=eps.cuda(), use_graph=True)
+    for m in O.MODULES:
+        assert torch.equal(eng.arena[m].flat, snap[m][0]), f"{m}: lr=0 was ignored by a replayed graph"
+
+
+def test_fp32_two_steps_weights_tight():
+    """Exact-fp32 mode, two consecutive steps: the second Adam update depends on gradient MAGNITUDES (m, v mix two
+    gradients), so post-step weights are a real check of the optimiser arithmetic (models/p2p_model.py:273-280)."""
+    from p2pvg_b200._lib import kernels_for
+    T, B = 5, 3
+    cfg, state, opt, x, probs, eps = dcgan_case(T, B, {}, 0)
+    eng = TrainEngine(O.clone_state(state), cfg, opt, kernels_for("cuda"), act_dtype=torch.float32)
+    adam = {m: O.new_adam_state(state[m]) for m in O.MODULES}
+    x2 = torch.rand(T, B, 1, 64, 64, generator=torch.Generator().manual_seed(6))
+    for xi, seed in ((x, 11), (x2, 12)):
+        e = O.draw_eps(T - 1, B, 10, seed=seed)
+        ref = O.train_step(state, adam, xi, opt, 64, e, probs, mode="A")
+        got = eng.step(xi.cuda(), probs=probs, eps=e.cuda())
+    np.testing.assert_allclose(got, np.array(ref["losses"], dtype=np.float32), rtol=2e-3, atol=1e-6)
+    for m in O.MODULES:
+        for k, gref in ref["grads"][m].items():
+            if bn_cancelled_bias(m, k):
+                continue
+            dw = (eng.arena[m].p[k].cpu() - state[m][k]).abs()
+            solid = gref.abs() > 3e-2 * (gref.abs().max() + 1e-30)
+            assert dw[solid].max().item() <= 1e-4, f"{m}.{k}: {dw[solid].max().item():.3e} after two steps"
+
+
+def test_vgg64_bf16_batch32_vs_oracle():
+    """BASELINE configs[2] backbone in the benched mode at a batch where BatchNorm statistics are not noise-dominated."""
+    from p2pvg_b200._lib import kernels_for
+    from p2pvg_b200.engine_vgg import TrainEngineVGG
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    T, B = 6, 32
+    cfg = dict(CFG64, channels=3, image_width=64, backbone="vgg")
+    state = O.build_state(cfg, seed=1)
+    opt = O.default_opt(batch_size=B)
+    eng = TrainEngineVGG(O.clone_state(state), cfg, opt, kernels_for("cuda"), act_dtype=torch.bfloat16)
+    x = torch.rand(T, B, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    probs = np.random.RandomState(0).uniform(0, 1, T - 1)
+    eps = O.draw_eps(T - 1, B, 10, seed=11)
+    got = eng.step(x.cuda(), probs=probs, eps=eps.cuda())
+    adam = {m: O.new_adam_state(state[m]) for m in O.MODULES}
+    ref = O.train_step(state, adam, x, opt, "vgg", eps, probs, mode="A")
+    vgg_cancelled = lambda m, k: k.endswith("main.0.bias") or k in ("c5.0.bias", "upc1.0.bias")  # noqa: E731
+    worst = check_step(ref, state, got, eng, 1e-2, 0.99, "vgg64/bf16/B32", cancelled=vgg_cancelled)
+    print("worst cosines", worst)
+
+
+def test_h36m_rnn512_bf16_vs_oracle():
+    """BASELINE configs[4] recurrent size (rnn_size 512) in the benched mode."""
+    from p2pvg_b200._lib import kernels_for
+    from p2pvg_b200.engine_mlp import TrainEngineMLP
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    T, B = 12, 32
+    cfg = dict(g_dim=128, z_dim=10, rnn_size=512, backbone="mlp", predictor_rnn_layers=2, posterior_rnn_layers=1, prior_rnn_layers=1)
+    state = O.build_state(cfg, seed=1)
+    opt = O.default_opt(batch_size=B)
+    eng = TrainEngineMLP(O.clone_state(state), cfg, opt, kernels_for("cuda"), act_dtype=torch.bfloat16)
+    x = 3 * torch.randn(T, B, 17, 3, generator=torch.Generator().manual_seed(5))
+    probs = np.random.RandomState(0).uniform(0, 1, T - 1)
+    eps = O.draw_eps(T - 1, B, 10, seed=11)
+    snap = snapshot(eng)
+    for _ in range(2):
+        eng.step(x.cuda(), probs=probs, eps=eps.cuda(), use_graph=True)
+    restore(eng, snap)
+    got = eng.step(x.cuda(), probs=probs, eps=eps.cuda(), use_graph=True)
+    adam = {m: O.new_adam_state(state[m]) for m in O.MODULES}
+    ref = O.train_step(state, adam, x, opt, "mlp", eps, probs, mode="A")
+    worst = check_step(ref, state, got, eng, 1e-2, 0.995, "h36m/R512/bf16", cancelled=lambda m, k: False)
+    print("worst cosines", worst)
