@@ -100,3 +100,33 @@ class DevicePrefetcher:
         ev.record(torch.cuda.current_stream(self.device))
         self.free_ev[k] = ev
         self._fill()
+
+
+def bind_host_to_gpu(index: int):
+    """Restrict this process to the CPU cores local to GPU `index` (NVML's ideal CPU affinity), so that pinned staging
+    buffers are first-touched on the GPU's NUMA node and the H2D copies run at full PCIe rate.  Returns the previous
+    affinity set (to restore with os.sched_setaffinity(0, prev)), or None when nothing was changed."""
+    import os
+    if not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            ent = vis.split(",")[index].strip()
+            if ent.isdigit():
+                phys = int(ent)
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus or cpus == prev:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None

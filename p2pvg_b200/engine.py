@@ -416,29 +416,62 @@ class TrainEngine:
 
     def _run_inner(self, x, plan):
         self._mark("start")
-        self.pack_weights()
-        self.pack_lstm_weights()
-        self._mark("pack")
-        self.encode(x, plan)
-        self._mark("encode_fwd")
-        self.recurrent_fwd(plan)
-        self._mark("lstm_fwd")
-        self.decode(plan)
-        self.losses_fwd(plan)
-        self._mark("decode_fwd")
-        self.backward_main(plan)
-        self._mark("encoder_bwd")
+        for name, fn in self.phases(x, plan):
+            fn()
+            self._mark(name)
+
+    def phases(self, x, plan):
+        """The step as an ordered list of (name, thunk).  _run executes them back to back; time_phases() captures each
+        one into its own CUDA graph to time it without launch gaps (bench.py: LSTM-phase roofline)."""
+        non_prior = ("frame_predictor", "posterior", "encoder", "decoder")
+
+        def adam4():
+            self.adam(non_prior)
+            if self.mode == "A":   # backward #2 runs through the UPDATED decoder / predictor weights (SURVEY.md §0.5)
+                self.pack_weights(("decoder",))
+                self.pack_lstm_weights()
+
+        ph = [("pack", lambda: (self.pack_weights(), self.pack_lstm_weights())),
+              ("encode_fwd", lambda: self.encode(x, plan)),
+              ("lstm_fwd", lambda: self.recurrent_fwd(plan)),
+              ("decode_fwd", lambda: (self.decode(plan), self.losses_fwd(plan))),
+              ("decoder_bwd", lambda: self.backward_decoder(plan)),
+              ("lstm_bwd", lambda: self.backward_recurrent(plan)),
+              ("encoder_bwd", lambda: self.encoder_backward(plan))]
         if self.mode == "A":
-            self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
-            self.pack_weights(("decoder",))
-            self.pack_lstm_weights()
-            self._mark("adam4+repack")
-            self.backward_prior(plan)
+            ph += [("adam4+repack", adam4), ("prior_bwd", lambda: self.backward_prior(plan))]
         else:
-            self.backward_prior(plan)
-            self.adam(("frame_predictor", "posterior", "encoder", "decoder"))
-        self._mark("prior_bwd")
-        self.adam(("prior",))
+            ph += [("prior_bwd", lambda: self.backward_prior(plan)), ("adam4", adam4)]
+        ph.append(("adam_prior", lambda: self.adam(("prior",))))
+        return ph
+
+    def time_phases(self, x, reps=5):
+        """Device time (ms) of every phase of a step on batch `x`, each phase captured into its own CUDA graph and
+        replayed `reps` times between CUDA events.  Leaves the optimiser / BatchNorm state advanced: measurement only.
+        No collectives (single-rank measurement)."""
+        plan = self.last_plan
+        saved, self.dist = self.dist, None
+        out = {}
+        try:
+            self._run(x, plan)   # eager: every buffer exists, activations of this batch are in place
+            torch.cuda.synchronize(self.dev)
+            for name, fn in self.phases(x, plan):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                g.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize(self.dev)
+                out[name] = e0.elapsed_time(e1) / reps
+                del g
+        finally:
+            self.dist = saved
+            self._graphs.clear()
+        return out
 
     # -- Phase E ----------------------------------------------------------------------------
     def encode(self, x, plan):
@@ -881,14 +914,13 @@ class TrainEngine:
             K.colsum(dlv, rows, z, z, A.g["logvar_net.bias"])
         return dtop
 
-    def backward_main(self, plan):
-        """loss = mse + beta*kld + weight_align*align  (models/p2p_model.py:261-262)."""
+    def backward_decoder(self, plan):
+        """loss = mse + beta*kld + weight_align*align  (models/p2p_model.py:261-262): decoder part + the loss scalars."""
         K, B, S, g, z, R, T = self.K, self.B, self.S, self.g, self.z, self.R, self.T
         opt = self.opt
         self.d_hpred[:(S + 1) * B * g].zero_()
         self.dH[:T * B * g].zero_()
         self.decoder_backward(0, S, want_wgrad=True, want_skip=True)
-        self._mark("decoder_bwd")
         # alignment loss (value + gradients into d_hpred / dH)
         K.align(self.Hlat, self.ix["in_idx"], self.h_pred, S - 1, B, g, float(opt["weight_align"]), self.align_partial,
                 self.d_hpred, self.dH)
@@ -897,6 +929,11 @@ class TrainEngine:
         E = B * self.frame_elems
         K.finalize_losses(self.mse_partial, S, plan.has_cpc, E, self.kl_sum, float(opt["batch_size"]), self.align_partial,
                           max(S - 1, 0), float(T), self.loss_out)
+
+    def backward_recurrent(self, plan):
+        """Backward #1 through the three LSTMs: d h_pred -> frame predictor -> (z) -> posterior / prior -> dH."""
+        K, B, S, g, z, R, T = self.K, self.B, self.S, self.g, self.z, self.R, self.T
+        opt = self.opt
         # frame predictor (recon steps only; the CPC step has no cotangent in this pass)
         A = self.arena["frame_predictor"]
         rows = S * B
@@ -928,8 +965,6 @@ class TrainEngine:
         K.gather_add_cols(self.dH, dXprior, ix["in_idx"], S, T, B, g, win, 0)
         K.gather_add_cols(self.dH, dXprior, ix["glob_idx"], S, T, B, g, win, g)
         K.gather_add_cols(self.dH, dXpred, ix["in_idx"], S, T, B, g, wp, 0)
-        self._mark("lstm_bwd")
-        self.encoder_backward(plan)
 
     def encoder_backward(self, plan):
         K, T, B, n, g = self.K, self.T, self.B, self.n, self.g
