@@ -22,6 +22,7 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+struct p2pvg_conv_fusion;
 
 #define P2PVG_OK 0
 #define P2PVG_ERR_BAD_ARG -1
@@ -83,7 +84,27 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
  * Returns P2PVG_ERR_UNSUPPORTED for shapes outside the pixel-box tiling (channels not a multiple of 64, ...). */
 int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c, int c_dtype, int64_t ldc, int N, int H, int W, int Ck,
                     int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
-                    void* workspace, size_t ws_bytes, void* stream);
+                    void* workspace, size_t ws_bytes, const struct p2pvg_conv_fusion* fusion, void* stream);
+
+/* Optional epilogue fusions of p2pvg_conv_gemm (kinds 0, 2, 3, 5; `fusion` may be NULL, every member may be NULL).
+ * nn.BatchNorm2d in training mode sits between every pair of convolutions (models/dcgan_64.py:9,21, models/vgg_64.py:9): its
+ * batch statistics need the whole convolution output, so the producing GEMM emits them from its accumulator registers
+ * instead of a separate pass over the stored tensor.
+ *   fwd_stat_partial  out, float2 [pixel tile of 128 output rows x phase (kind 2: 4 output parities, else 1)][Cn]:
+ *                     (sum y, sum y^2) of the tile's rows, y as stored (bf16-rounded for a bf16 output).  The tile of GEMM
+ *                     row block mt and phase ph is row mt*phases + ph; reduce per group with p2pvg_bn_fwd_finalize_tiles
+ *                     (rows of one BatchNorm group must be a multiple of 128).
+ *   bwd_*             reserved for the BatchNorm-backward reduction of a data-gradient GEMM (sum dz, sum dz*xhat). */
+typedef struct p2pvg_conv_fusion {
+  void* fwd_stat_partial;
+  const void* bwd_raw;
+  const float* bwd_mean;
+  const float* bwd_invstd;
+  const float* bwd_scale;
+  const float* bwd_shift;
+  void* bwd_stat_partial;
+  int64_t rows_per_group;
+} p2pvg_conv_fusion_t;
 
 /* vgg_64 data movement (models/vgg_64.py), NHWC, dtype f32 | bf16.
  *   im2col3  : col[(n,y,x), tap*C + c] = x[n, y + sgn*(kh-1), x + sgn*(kw-1), c], row pitch ld >= 9C (pad columns zeroed);
@@ -144,6 +165,19 @@ int p2pvg_bn_act(const void* x, void* y, int dtype, const float* scale, const fl
 int p2pvg_bn_bwd(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
                  const float* gamma, int G, int64_t R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
                  float* sum_dzx, const float* scale, const float* shift, void* stream);
+/* The same two BatchNorm reductions when their per-tile column sums were produced by a GEMM epilogue (p2pvg_conv_fusion):
+ * partial is float2 [G * parts_per_group][ldp]; channel c of group g sums the group's partial rows over the `fold` column
+ * groups f*C + c (a GEMM row may hold several pixels / filter taps of one channel).  R = elements per (group, channel).
+ * fp64 combine in a fixed order (deterministic).  Replaces the statistics pass of nn.BatchNorm2d (models/dcgan_64.py:9). */
+int p2pvg_bn_fwd_finalize_tiles(const void* partial, int parts_per_group, int ldp, int fold, int G, int64_t R, int C,
+                                const float* gamma, const float* beta, float eps, float* mean, float* invstd, float* var_unbiased,
+                                float* scale, float* shift, void* stream);
+int p2pvg_bn_bwd_finalize_tiles(const void* partial, int parts_per_group, int ldp, int fold, int G, int C, float* sum_dz,
+                                float* sum_dzx, void* stream);
+/* apply pass of the BatchNorm + activation backward alone (the per-channel sums sum_dz / sum_dzx are given) */
+int p2pvg_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
+                       const float* gamma, int G, int64_t R, int C, int act, void* dx, const float* sum_dz, const float* sum_dzx,
+                       const float* scale, const float* shift, void* stream);
 /* eval-mode BatchNorm (running statistics; generate.py / p2p_generate): scale = gamma/sqrt(rvar+eps), shift = beta-rmean*scale */
 int p2pvg_bn_eval_coeffs(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, int C,
                          float* scale, float* shift, void* stream);

@@ -498,6 +498,70 @@ def forward_losses(state, x, opt, width, eps, probs, tape=None):
     return mse, kld, cpc, align
 
 
+
+def p2p_generate(state, x, len_output, eval_cp_ix, opt, width, eps, probs, model_mode="full", skip_frame=False):
+    """models/p2p_model.py:80-183 — autoregressive point-to-point generation, modules in eval mode (BatchNorm uses its
+    running statistics: train.py:245, generate.py:82).  One sample per input sequence; skipped frames are zeros (:136);
+    the posterior sees ground truth only while it exists (:167-171); model_mode picks the z that feeds the predictor
+    (:159-162, :176-179).  ``eps``: [n_executed, 2, B, z] — posterior's draw then prior's draw per executed step
+    (both gaussian LSTMs are called every executed step); ``probs``: the np.random.uniform(0,1,len_output-1) draw (:128).
+    Returns the list of len_output frames."""
+    enc, dec = state["encoder"], state["decoder"]
+    fp, post, prior = state["frame_predictor"], state["posterior"], state["prior"]
+    if width == "mlp":
+        encoder_fwd_ = lambda p, xx: mlp_encoder_fwd(p, xx)
+        decoder_fwd_ = lambda p, v, sk: mlp_decoder_fwd(p, v, sk)
+    elif width == "vgg":
+        encoder_fwd_ = lambda p, xx: vgg_encoder_fwd(p, xx, training=False)
+        decoder_fwd_ = lambda p, v, sk: vgg_decoder_fwd(p, v, sk, training=False)
+    else:
+        encoder_fwd_ = lambda p, xx: encoder_fwd(p, xx, width, training=False)
+        decoder_fwd_ = lambda p, v, sk: decoder_fwd(p, v, sk, width, training=False)
+    with torch.no_grad():
+        B = x[0].shape[0]
+        gen_seq = [x[0]]
+        x_in = x[0]
+        hid_fp, hid_post, hid_prior = init_hidden(fp, B, x[0]), init_hidden(post, B, x[0]), init_hidden(prior, B, x[0])
+        seq_len = len(x)
+        x_cp = x[seq_len - 1]
+        global_z = encoder_fwd_(enc, x_cp)[0]
+        prev_i, skip_count, s = 0, 0, 0
+        max_skip_count = seq_len * opt["skip_prob"]
+        skip = None
+        for i in range(1, len_output):
+            if (probs[i - 1] <= opt["skip_prob"] and i >= opt["n_past"] and skip_count < max_skip_count and i != 1
+                    and i != (len_output - 1) and skip_frame):
+                skip_count += 1
+                gen_seq.append(torch.zeros_like(x_in))
+                continue
+            tuc = x_cp.new_zeros(B, 1).fill_((eval_cp_ix - i + 1) / eval_cp_ix)
+            dt = x_cp.new_zeros(B, 1).fill_((i - prev_i) / eval_cp_ix)
+            prev_i = i
+            h, sk = encoder_fwd_(enc, x_in)
+            if opt["last_frame_skip"] or i == 1 or i < opt["n_past"]:
+                skip = sk
+            h_cpaw = torch.cat([h, global_z, tuc, dt], 1)
+            if i < opt["n_past"]:
+                h_target = encoder_fwd_(enc, x[i])[0]
+                zt = gaussian_lstm_fwd(post, hid_post, torch.cat([h_target, global_z, tuc, dt], 1), eps[s, 0])[0]
+                zt_p = gaussian_lstm_fwd(prior, hid_prior, h_cpaw, eps[s, 1])[0]
+                lstm_fwd(fp, hid_fp, torch.cat([h, zt if model_mode in ("posterior", "full") else zt_p, tuc, dt], 1))
+                x_in = x[i]
+            else:
+                if i < len(x):
+                    h_target = encoder_fwd_(enc, x[i])[0]
+                    h_target_cpaw = torch.cat([h_target, global_z, tuc, dt], 1)
+                else:
+                    h_target_cpaw = h_cpaw
+                zt = gaussian_lstm_fwd(post, hid_post, h_target_cpaw, eps[s, 0])[0]
+                zt_p = gaussian_lstm_fwd(prior, hid_prior, h_cpaw, eps[s, 1])[0]
+                h_pred = lstm_fwd(fp, hid_fp, torch.cat([h, zt if model_mode == "posterior" else zt_p, tuc, dt], 1))
+                x_in = decoder_fwd_(dec, h_pred, skip)
+            s += 1
+            gen_seq.append(x_in)
+    return gen_seq
+
+
 def train_step(state, adam, x, opt, width, eps, probs, mode="A", tape=None):
     """One call of P2PModel.forward (models/p2p_model.py:185-271).
 

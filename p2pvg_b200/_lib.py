@@ -58,6 +58,13 @@ def _p(t):
     return _vp(t.data_ptr())
 
 
+class ConvFusion(ctypes.Structure):
+    """p2pvg_conv_fusion_t (include/p2pvg_b200.h)."""
+    _fields_ = [("fwd_stat_partial", ctypes.c_void_p), ("bwd_raw", ctypes.c_void_p), ("bwd_mean", ctypes.c_void_p),
+                ("bwd_invstd", ctypes.c_void_p), ("bwd_scale", ctypes.c_void_p), ("bwd_shift", ctypes.c_void_p),
+                ("bwd_stat_partial", ctypes.c_void_p), ("rows_per_group", ctypes.c_int64)]
+
+
 class _Workspaces:
     """Scratch buffers of one device, shared by every CudaKernels view of it.  ``gen`` counts re-allocations: a captured
     CUDA graph that used a workspace is stale once it moved (TrainEngine.graph_generation)."""
@@ -161,17 +168,21 @@ class CudaKernels:
 
     # -- implicit-GEMM convolutions ---------------------------------------------------------
     def conv_gemm(self, kind, a, b, c, N, H, W, Ck, Cn, Cm=0, ldb=None, ldc=None, bias=None, addend=None, grp_src=None,
-                  imgs_per_group=0, accumulate=False):
-        """kind 0/1/2 of p2pvg_conv_gemm (see include/p2pvg_b200.h).  H, W: small-map size."""
+                  imgs_per_group=0, accumulate=False, stat_partial=None):
+        """kind 0..5 of p2pvg_conv_gemm (see include/p2pvg_b200.h).  H, W: small-map size.  stat_partial: fp32 buffer of
+        [tiles * phases, Cn, 2] receiving the BatchNorm forward statistics of the output (epilogue fusion)."""
         taps = 9 if kind >= 3 else 16
         if ldb is None:
             ldb = taps * Ck if kind in (0, 3, 5) else taps * Cn
         if ldc is None:
             ldc = taps * Cn if kind in (1, 4) else Cn
         ws = self.gemm_workspace()
+        fusion = None
+        if stat_partial is not None:
+            fusion = ctypes.byref(ConvFusion(fwd_stat_partial=stat_partial.data_ptr()))
         self._ck(self.lib.p2pvg_conv_gemm(_i(kind), _p(a), _p(b), _i64(ldb), _p(c), _i(_dt(c)), _i64(ldc), _i(N), _i(H), _i(W), _i(Ck),
                                           _i(Cn), _i(Cm), _p(bias), _p(addend), _p(grp_src), _i(imgs_per_group), _i(int(accumulate)),
-                                          _p(ws), _sz(ws.numel()), self._stream()))
+                                          _p(ws), _sz(ws.numel()), fusion, self._stream()))
 
     def conv_thin_in(self, x, w, bias, y, N, H, W, Ci, Co):
         self._ck(self.lib.p2pvg_conv_thin_in(_p(x), _i(_dt(x)), _p(w), _p(bias), _p(y), _i(N), _i(H), _i(W), _i(Ci), _i(Co), self._stream()))
@@ -233,6 +244,19 @@ class CudaKernels:
         self._ck(self.lib.p2pvg_bn_fwd_stats(_p(x), _i(_dt(x)), _i(G), _i64(R), _i(C), _p(gamma), _p(beta), _f(eps), _p(ws),
                                              _sz(ws.numel()), _p(mean), _p(invstd), _p(var_unb), _p(scale), _p(shift),
                                              self._stream()))
+
+    def bn_fwd_finalize_tiles(self, partial, parts_per_group, ldp, fold, G, R, C, gamma, beta, mean, invstd, var_unb, scale, shift, eps=1e-5):
+        self._ck(self.lib.p2pvg_bn_fwd_finalize_tiles(_p(partial), _i(parts_per_group), _i(ldp), _i(fold), _i(G), _i64(R), _i(C), _p(gamma),
+                                                      _p(beta), _f(eps), _p(mean), _p(invstd), _p(var_unb), _p(scale), _p(shift),
+                                                      self._stream()))
+
+    def bn_bwd_finalize_tiles(self, partial, parts_per_group, ldp, fold, G, C, sum_dz, sum_dzx):
+        self._ck(self.lib.p2pvg_bn_bwd_finalize_tiles(_p(partial), _i(parts_per_group), _i(ldp), _i(fold), _i(G), _i(C), _p(sum_dz),
+                                                      _p(sum_dzx), self._stream()))
+
+    def bn_bwd_apply(self, dy, x, y, mean, invstd, gamma, G, R, C, act, dx, sum_dz, sum_dzx, scale=None, shift=None):
+        self._ck(self.lib.p2pvg_bn_bwd_apply(_p(dy), _p(x), _p(y), _i(_dt(x)), _p(mean), _p(invstd), _p(gamma), _i(G), _i64(R), _i(C),
+                                             _i(act), _p(dx), _p(sum_dz), _p(sum_dzx), _p(scale), _p(shift), self._stream()))
 
     def bn_act(self, x, y, scale, shift, G, R, C, act):
         self._ck(self.lib.p2pvg_bn_act(_p(x), _p(y), _i(_dt(x)), _p(scale), _p(shift), _i(G), _i64(R), _i(C), _i(act), self._stream()))

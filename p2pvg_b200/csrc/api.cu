@@ -43,7 +43,12 @@ int p2pvg_conv_thin_in_impl(const void*, int, const float*, const float*, void*,
 int p2pvg_convT_thin_out_impl(const void*, int, const float*, const float*, const float*, const int*, int, void*, int, int, int, int, int,
                               int, cudaStream_t);
 int p2pvg_conv_gemm_impl(int, const void*, const void*, long long, void*, int, long long, int, int, int, int, int, int, const float*,
-                         const float*, const int*, int, int, void*, size_t, cudaStream_t);
+                         const float*, const int*, int, int, void*, size_t, void*, cudaStream_t);
+int p2pvg_bn_fwd_finalize_tiles_impl(const void*, int, int, int, int, long long, int, const float*, const float*, float, float*, float*, float*,
+                                     float*, float*, cudaStream_t);
+int p2pvg_bn_bwd_finalize_tiles_impl(const void*, int, int, int, int, int, float*, float*, cudaStream_t);
+int p2pvg_bn_bwd_apply_impl(const void*, const void*, const void*, int, const float*, const float*, const float*, int, long long, int, int,
+                            void*, const float*, const float*, const float*, const float*, cudaStream_t);
 int p2pvg_im2col_k4s2p1_impl(const void*, void*, int, int, int, int, int, cudaStream_t);
 int p2pvg_im2col3_impl(const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int p2pvg_col2im3_impl(const void*, void*, int, int, int, int, int, int, const float*, cudaStream_t);
@@ -136,10 +141,13 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
 
 int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c, int c_dtype, int64_t ldc, int N, int H, int W, int Ck,
                     int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
-                    void* workspace, size_t ws_bytes, void* stream) {
+                    void* workspace, size_t ws_bytes, const p2pvg_conv_fusion_t* fusion, void* stream) {
   P2PVG_REQUIRE(a && b && c, P2PVG_ERR_BAD_ARG, "conv_gemm: null operand");
+  void* fwd_stat = fusion ? fusion->fwd_stat_partial : nullptr;
+  P2PVG_REQUIRE(!fusion || fusion->bwd_stat_partial == nullptr, P2PVG_ERR_UNSUPPORTED, "conv_gemm: backward BatchNorm fusion is reserved");
+  P2PVG_REQUIRE(!(fwd_stat && accumulate), P2PVG_ERR_BAD_ARG, "conv_gemm: statistics of an accumulating GEMM are not defined");
   return p2pvg_conv_gemm_impl(kind, a, b, ldb, c, c_dtype, ldc, N, H, W, Ck, Cn, Cm, bias, addend, grp_src, imgs_per_group, accumulate,
-                              workspace, ws_bytes, ST);
+                              workspace, ws_bytes, fwd_stat, ST);
 }
 
 int p2pvg_conv_thin_in(const void* x, int dtype, const float* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,
@@ -209,6 +217,21 @@ int p2pvg_bn_bwd(const void* dy, const void* x, const void* y, int dtype, const 
                  const float* gamma, int G, int64_t R, int C, int act, void* ws, size_t ws_bytes, void* dx, float* sum_dz,
                  float* sum_dzx, const float* scale, const float* shift, void* stream) {
   return p2pvg_bn_bwd_impl(dy, x, y, dtype, mean, invstd, gamma, G, R, C, act, ws, ws_bytes, dx, sum_dz, sum_dzx, scale, shift, ST);
+}
+int p2pvg_bn_fwd_finalize_tiles(const void* partial, int parts_per_group, int ldp, int fold, int G, int64_t R, int C,
+                                const float* gamma, const float* beta, float eps, float* mean, float* invstd, float* var_unbiased,
+                                float* scale, float* shift, void* stream) {
+  return p2pvg_bn_fwd_finalize_tiles_impl(partial, parts_per_group, ldp, fold, G, R, C, gamma, beta, eps, mean, invstd, var_unbiased, scale,
+                                          shift, ST);
+}
+int p2pvg_bn_bwd_finalize_tiles(const void* partial, int parts_per_group, int ldp, int fold, int G, int C, float* sum_dz,
+                                float* sum_dzx, void* stream) {
+  return p2pvg_bn_bwd_finalize_tiles_impl(partial, parts_per_group, ldp, fold, G, C, sum_dz, sum_dzx, ST);
+}
+int p2pvg_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, const float* mean, const float* invstd,
+                       const float* gamma, int G, int64_t R, int C, int act, void* dx, const float* sum_dz, const float* sum_dzx,
+                       const float* scale, const float* shift, void* stream) {
+  return p2pvg_bn_bwd_apply_impl(dy, x, y, dtype, mean, invstd, gamma, G, R, C, act, dx, sum_dz, sum_dzx, scale, shift, ST);
 }
 int p2pvg_bn_param_grad(const float* sum_dz, const float* sum_dzx, int G, int C, float* dgamma, float* dbeta, void* stream) {
   return p2pvg_bn_param_grad_impl(sum_dz, sum_dzx, G, C, dgamma, dbeta, ST);

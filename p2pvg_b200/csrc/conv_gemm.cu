@@ -64,7 +64,8 @@ template <int KIND, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv, int c_bf16,
                  long long ldc, Geom g, int accumulate, const float* __restrict__ bias, const float* __restrict__ addend,
-                 const int* __restrict__ grp_src, float* __restrict__ partial, int kb_per_split, int splits) {
+                 const int* __restrict__ grp_src, float* __restrict__ partial, int kb_per_split, int splits,
+                 float2* __restrict__ stat_partial) {
   using C_ = Cfg<BN>;
   constexpr bool A_MN = (KIND == 1), B_MN = (KIND != 0);
   constexpr int UMMA_K = 16;
@@ -234,6 +235,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue =====================
     const int q = warp & 3;
     __shared__ float bias_s[2 * BN];
+    // BatchNorm forward statistics fused into the epilogue: per-warp column sums (sum y, sum y^2) of the tile, double-
+    // buffered by accumulator so that tile t+1 may write while the sums of tile t are still being combined
+    __shared__ float2 stat_s[(KIND == 1) ? 1 : 2 * 4 * BN];
+    const bool do_stat = (KIND != 1) && stat_partial != nullptr;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
       const int ph = (KIND == 2) ? (t & 3) : 0;
@@ -307,7 +312,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int c = pr * 2 + h;
           const uint32_t* v = v2 + 32 * h;
           const int nbase = n0 + c * 32;
-          if (!row_ok || nbase >= g.Ntot) continue;
+          if (nbase >= g.Ntot) continue;             // warp-uniform
+          if (!row_ok && !do_stat) continue;         // rows past the end only matter as zeros of the column sums
           if (KIND == 1 && partial != nullptr) {
             float* dst = partial + ((long long)z * g.M + out_row) * g.Ntot + nbase;
 #pragma unroll
@@ -332,6 +338,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float4 x4 = a4[8 * h + j];
               f[4 * j] += x4.x; f[4 * j + 1] += x4.y; f[4 * j + 2] += x4.z; f[4 * j + 3] += x4.w;
             }
+          }
+          if (KIND != 1 && do_stat) {
+            // statistics of the tensor AS STORED (bf16-rounded when the output is bf16); all 32 lanes take part
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float r = row_ok ? (c_bf16 ? bf16_round(f[j]) : f[j]) : 0.f;
+              s1[j] = r;
+              s2[j] = r * r;
+            }
+            const float cs = warp_colsum32(s1, lane), cq = warp_colsum32(s2, lane);
+            stat_s[(acc * 4 + q) * BN + c * 32 + lane] = make_float2(cs, cq);
+            if (!row_ok) continue;
           }
           if (c_bf16) {
             bf16* crow = reinterpret_cast<bf16*>(Cv) + out_row * ldc + nbase;
@@ -372,6 +391,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             }
           }
+        }
+      }
+      if (KIND != 1 && do_stat) {
+        // combine the four warps' column sums in a fixed order (deterministic) -> one partial row per (pixel tile, phase)
+        epi_bar_sync();
+        float2* dst = stat_partial + ((long long)mt * phases + ph) * g.Ntot + n0;
+        for (int i = q * 32 + lane; i < BN; i += 128) {
+          if (n0 + i >= g.Ntot) continue;
+          const float2 a = stat_s[(acc * 4 + 0) * BN + i], b = stat_s[(acc * 4 + 1) * BN + i];
+          const float2 c2 = stat_s[(acc * 4 + 2) * BN + i], d = stat_s[(acc * 4 + 3) * BN + i];
+          dst[i] = make_float2((a.x + b.x) + (c2.x + d.x), (a.y + b.y) + (c2.y + d.y));
         }
       }
     }
@@ -465,7 +495,8 @@ bool box_for(int P, int H, int W, int& bh, int& bn) {
 
 template <int KIND, int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, const Geom& g, int accumulate,
-           const float* bias, const float* addend, const int* grp_src, float* partial, int splits, int kb_per_split, cudaStream_t st) {
+           const float* bias, const float* addend, const int* grp_src, float* partial, int splits, int kb_per_split, cudaStream_t st,
+           float2* stat_partial = nullptr) {
   auto kern = conv_gemm_kernel<KIND, BN>;
   int& done = g_attr[KIND][BN == 256 ? 2 : BN == 128];
   if (!done) {
@@ -479,7 +510,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, l
   long long tiles = (long long)cdiv(g.M, BLOCK_M) * cdiv(g.Ntot, BN) * splits * (KIND == 2 ? 4 : 1);
   int grid = (int)(tiles < g_sms ? tiles : g_sms);
   kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, C, c_dtype == P2PVG_BF16, ldc, g, accumulate, bias, addend, grp_src, partial,
-                                                      kb_per_split, splits);
+                                                      kb_per_split, splits, stat_partial);
   return p2pvg_check_launch("conv_gemm");
 }
 
@@ -489,7 +520,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, l
 // fit the pixel-box tiling (the caller then uses the explicit im2col / col2im path).
 int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, void* c, int c_dtype, long long ldc, int N, int H, int W,
                          int Ck, int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group,
-                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+                         int accumulate, void* ws, size_t ws_bytes, void* stat_partial_v, cudaStream_t st) {
+  float2* stat_partial = reinterpret_cast<float2*>(stat_partial_v);
   std::call_once(g_once2, resolve2);
   P2PVG_REQUIRE(g_enc != nullptr, P2PVG_ERR_UNSUPPORTED, "conv_gemm: cuTensorMapEncodeTiled unavailable");
   P2PVG_REQUIRE(kind >= 0 && kind <= 5, P2PVG_ERR_BAD_ARG, "conv_gemm: bad kind %d", kind);
@@ -529,9 +561,9 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
     rc = map2d(&tb, b, (long long)taps * Ck, Cn, ldb, BN);
     if (rc) return rc;
     const int nkb = taps * (Ck / 64);
-    if (BN == 256) return launch<0, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
-    if (BN == 128) return launch<0, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
-    return launch<0, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
+    if (BN == 256) return launch<0, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
+    if (BN == 128) return launch<0, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
+    return launch<0, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
   }
   if (kind == 2) {
     g.M = (int)pix; g.Ntot = Cn;
@@ -541,12 +573,13 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
     if (rc) return rc;
     const int nkb = 4 * (Ck / 64);
     const int BN = (Cn % 256 == 0 && g_bn256) ? 256 : Cn > 64 ? 128 : 64;
-    if (BN == 256) return launch<2, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
-    if (BN == 128) return launch<2, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
-    return launch<2, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st);
+    if (BN == 256) return launch<2, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
+    if (BN == 128) return launch<2, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
+    return launch<2, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
   }
   // kind 1: weight gradient
   P2PVG_REQUIRE(c_dtype == P2PVG_F32, P2PVG_ERR_BAD_ARG, "conv_gemm kind 1 writes fp32");
+  P2PVG_REQUIRE(stat_partial == nullptr, P2PVG_ERR_BAD_ARG, "conv_gemm: BatchNorm statistics belong to the forward / data-gradient kinds");
   g.M = Cm; g.Ntot = taps * Cn; g.Ck = 64;
   rc = map2d(&ta, a, Cm, pix, Cm, 64);  // a_small [pix][Cm] as MN-major A
   if (rc) return rc;

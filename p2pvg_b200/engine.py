@@ -169,6 +169,9 @@ class TrainEngine:
         # stream (captured into the same CUDA graph) so that the TMA-bound wgrad GEMMs overlap the HBM-bound BatchNorm kernels
         # and the latency-bound LSTM scans of the main stream.  Measured gain on one B200: 1.3 % (24.57 -> 24.26 ms) -- the
         # persistent GEMMs leave little room for a co-resident kernel -- so it is opt-in: P2PVG_OVERLAP=1.
+        # BatchNorm forward statistics come out of the producing implicit GEMM's epilogue (per-tile column sums) instead of a
+        # separate pass over the stored tensor; P2PVG_BN_FUSE=0 keeps the stand-alone statistics kernel (A/B comparison)
+        self.fuse_stats = self.implicit and os.environ.get("P2PVG_BN_FUSE", "1") != "0"
         self.overlap = getattr(kernels, "name", "") == "cuda" and os.environ.get("P2PVG_OVERLAP", "0") == "1"
         self.side = None
         self._side_dirty = False
@@ -505,8 +508,11 @@ class TrainEngine:
             imp = self.implicit and cin % 64 == 0 and cout % 64 == 0
             col = None
             thin = self.thin and cin <= 4
+            sp = None
             if imp:
-                K.conv_gemm(0, a, self._packed[f"enc{l}"], raw, N, Ho, Ho, cin, cout, bias=P[cn + ".bias"])
+                sp = self.stat_buf(f"enc{l}", M, 1, cout, B * Ho * Ho)
+                K.conv_gemm(0, a, self._packed[f"enc{l}"], raw, N, Ho, Ho, cin, cout, bias=P[cn + ".bias"],
+                            stat_partial=sp["buf"] if sp else None)
             elif thin:  # 1/3-channel input: direct HBM-bound kernel on the fp32 master weights
                 K.conv_thin_in(a, P[cn + ".weight"], P[cn + ".bias"], raw, N, H, H, cin, cout)
             else:
@@ -516,7 +522,7 @@ class TrainEngine:
                     K.gemm(col, self._packed["enc0.bd"], raw, M // 4, 4 * cout, 64 * cin, bias=self._packed["enc0.bias4"])
                 else:
                     K.gemm(col, self._packed[f"enc{l}"], raw, M, cout, 16 * cin, bias=P[cn + ".bias"])
-            st = self.bn_forward("enc", l, raw, y, T, B * Ho * Ho, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
+            st = self.bn_forward("enc", l, raw, y, T, B * Ho * Ho, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU, tiles=sp)
             self.enc.append(dict(col=col, raw=raw, y=y, st=st, cin=cin, cout=cout, Hin=H, Hout=Ho, M=M, imp=imp, inp=a, thin=thin))
             a, H = y, Ho
         # final 4x4 valid conv == GEMM over the flattened 4x4xC map
@@ -542,12 +548,26 @@ class TrainEngine:
                      st["C"], BN_MOMENTUM)
             Bf[bn + ".num_batches_tracked"] += ncalls
 
-    def bn_forward(self, tag, idx, raw, y, G, R, C, gamma, beta, act):
+    def stat_buf(self, tag, rows, phases, C, rows_per_group):
+        """Workspace for the per-tile BatchNorm statistics of a GEMM epilogue, or None when the fusion does not apply
+        (a 128-row tile must not straddle two BatchNorm groups).  rows: GEMM rows (per phase)."""
+        if not self.fuse_stats or rows_per_group % 128 != 0 or rows % 128 != 0:
+            return None
+        buf = self.fbuf(f"bnpart_{tag}", (rows // 128) * phases * C * 2)
+        return dict(buf=buf, parts_per_group=(rows_per_group // 128) * phases, ldp=C, fold=1)
+
+    def bn_forward(self, tag, idx, raw, y, G, R, C, gamma, beta, act, tiles=None):
+        """Batch statistics per group + normalise + activation.  tiles: statistics partials already produced by the
+        epilogue of the GEMM that wrote `raw` (stat_buf) -- then only the tiny finalize kernel runs instead of a pass over raw."""
         K = self.K
         names = ("mean", "invstd", "varu", "scale", "shift", "sdz", "sdzx")
         st = {nm: self.fbuf(f"{tag}_bn{idx}_{nm}", G * C) for nm in names}
         st.update(G=G, R=R, C=C, act=act, gamma=gamma)
-        K.bn_fwd_stats(raw, G, R, C, gamma, beta, st["mean"], st["invstd"], st["varu"], st["scale"], st["shift"])
+        if tiles is not None:
+            K.bn_fwd_finalize_tiles(tiles["buf"], tiles["parts_per_group"], tiles["ldp"], tiles["fold"], G, R, C, gamma, beta,
+                                    st["mean"], st["invstd"], st["varu"], st["scale"], st["shift"])
+        else:
+            K.bn_fwd_stats(raw, G, R, C, gamma, beta, st["mean"], st["invstd"], st["varu"], st["scale"], st["shift"])
         K.bn_act(raw, y, st["scale"], st["shift"], G, R, C, act)
         return st
 
@@ -673,11 +693,14 @@ class TrainEngine:
             Mo = N * 4 * Hi * Hi
             raw = self.buf(f"dec_raw{k}", Mo * cout)
             imp = self.implicit and cd % 64 == 0 and cout % 64 == 0
+            sp = None
             if imp:
                 # skip half once per distinct source frame (fp32, bias folded in), added in the epilogue of the main GEMM
                 addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
                 K.conv_gemm(2, skip, wS, addS, nskip * B, Hi, Hi, cd, cout, bias=P[cn + ".bias"])
-                K.conv_gemm(2, d, wD, raw, N, Hi, Hi, cd, cout, addend=addS, grp_src=self.ix["skip_src"], imgs_per_group=B)
+                sp = self.stat_buf(f"dec{k}", Md, 4, cout, B * Hi * Hi) if k < n - 1 else None
+                K.conv_gemm(2, d, wD, raw, N, Hi, Hi, cd, cout, addend=addS, grp_src=self.ix["skip_src"], imgs_per_group=B,
+                            stat_partial=sp["buf"] if sp else None)
             elif self.thin and cout <= 3 and cd % 8 == 0:
                 w32 = P[cn + ".weight"]  # [2*cd, nc, 4, 4] fp32 master: rows [0,cd) act on d, rows [cd,2cd) on the skip
                 addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
@@ -697,7 +720,7 @@ class TrainEngine:
                        thin=(not imp) and self.thin and cout <= 3 and cd % 8 == 0)
             if k < n - 1:
                 dn = self.buf(f"dec_d{k}", Mo * cout)
-                rec["st"] = self.bn_forward("dec", k, raw, dn, G, B * 4 * Hi * Hi, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU)
+                rec["st"] = self.bn_forward("dec", k, raw, dn, G, B * 4 * Hi * Hi, cout, P[bn + ".weight"], P[bn + ".bias"], ACT_LRELU, tiles=sp)
                 rec["d"] = dn
                 d = dn
             self.dec.append(rec)

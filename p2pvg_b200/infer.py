@@ -26,6 +26,28 @@ def kernels_for(device):
     return _EXACT[base.device.index]
 
 
+_EPS_STREAM = None
+
+
+class eps_stream:
+    """Context manager: the reparameterisation noise of every gaussian_lstm call inside comes from `draws` (a list of
+    [B, z] tensors, consumed in call order) instead of torch.randn -- the reference draws from a global generator whose
+    stream cannot be reproduced across devices, so parity tests inject the reference's own draws."""
+
+    def __init__(self, draws):
+        self.draws = list(draws)
+
+    def __enter__(self):
+        global _EPS_STREAM
+        self.prev, _EPS_STREAM = _EPS_STREAM, self.draws
+        return self
+
+    def __exit__(self, *exc):
+        global _EPS_STREAM
+        _EPS_STREAM = self.prev
+        return False
+
+
 def _act_dtype():
     import os
     return torch.float32 if os.environ.get("P2PVG_PRECISION", "bf16") == "fp32" else torch.bfloat16
@@ -196,7 +218,10 @@ def gaussian_lstm_forward(mod, inp):
     mu, lv = torch.empty(B, z_dim, device=dev), torch.empty(B, z_dim, device=dev)
     K.gemm(h, mod.mu_net.weight.data, mu, B, z_dim, R, bias=mod.mu_net.bias.data)
     K.gemm(h, mod.logvar_net.weight.data, lv, B, z_dim, R, bias=mod.logvar_net.bias.data)
-    eps = torch.randn(B, z_dim, device=dev)  # the reference draws from the device's global generator (models/lstm.py:78)
+    if _EPS_STREAM is not None:   # parity tests replay the reference's own N(0,1) draws (eps_stream below)
+        eps = _EPS_STREAM.pop(0).to(device=dev, dtype=torch.float32).reshape(B, z_dim).contiguous()
+    else:
+        eps = torch.randn(B, z_dim, device=dev)  # the reference draws from the device's global generator (models/lstm.py:78)
     z, zz = torch.empty_like(mu), torch.empty_like(mu)
     kl = torch.zeros(4, device=dev)
     K.reparam_kl_fwd(mu, lv, mu, lv, eps, eps, z, zz, B * z_dim, kl)

@@ -58,6 +58,9 @@ class ArenaAdam(torch.optim.Optimizer):
     def load_state_dict(self, sd):
         arena = self._arena
         super().load_state_dict(sd)
+        for g in self.param_groups:   # checkpoints of older optimisers (e.g. PyTorch 1.0 Adam) lack newer hyper-parameter keys
+            for k, v in self.defaults.items():
+                g.setdefault(k, v)
         if arena is not None:  # re-home the loaded moments into the arena views
             names = {id(p): n for n, p in self._named}
             for p, st in list(self.state.items()):

@@ -78,3 +78,43 @@ def test_kind1_weight_gradient(K, N, H, Cm, Cn):
     out2 = out.clone()
     K.conv_gemm(1, nhwc(a), nhwc(b), out2, N, H, H, 0, Cn, Cm=Cm, accumulate=True)
     assert (out2 - 2 * ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 2e-2
+
+
+@pytest.mark.parametrize("kind,N,H,Ck,Cn,B", [(0, 16, 8, 64, 128, 4), (0, 32, 4, 128, 256, 8), (0, 6, 16, 64, 64, 2), (2, 16, 8, 128, 64, 4),
+                                               (2, 24, 4, 256, 128, 8), (2, 4, 16, 64, 256, 2), (0, 5, 8, 64, 128, 0)])
+def test_fused_batchnorm_statistics(K, kind, N, H, Ck, Cn, B):
+    """BatchNorm forward statistics from the GEMM epilogue (per-tile column sums + p2pvg_bn_fwd_finalize_tiles) against the
+    statistics of the stored bf16 output, per group of B images.  B = 0: one ragged group (rows not a multiple of 128):
+    only the per-tile sums are checked."""
+    torch.manual_seed(3)
+    Hin = 2 * H if kind == 0 else H
+    Hout = H if kind == 0 else 2 * H
+    x = (torch.randn(N, Hin, Hin, Ck, device="cuda") * 0.5).bfloat16()
+    taps = 16
+    wp = (torch.randn(Cn if kind == 0 else Ck, taps * (Ck if kind == 0 else Cn), device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(Cn, device="cuda")
+    out = torch.empty(N, Hout, Hout, Cn, device="cuda", dtype=torch.bfloat16)
+    phases = 4 if kind == 2 else 1
+    rows = N * H * H
+    ntiles = (rows + 127) // 128
+    part = torch.full((ntiles * phases, Cn, 2), float("nan"), device="cuda")
+    K.conv_gemm(kind, x, wp, out, N, H, H, Ck, Cn, bias=bias, stat_partial=part)
+    ref_out = torch.empty_like(out)
+    K.conv_gemm(kind, x, wp, ref_out, N, H, H, Ck, Cn, bias=bias)
+    assert torch.equal(out, ref_out), "the fused statistics must not change the stored output"
+    o = out.float()
+    tot = part.double().sum(0)
+    assert torch.isfinite(part).all()
+    s_ref, q_ref = o.double().sum((0, 1, 2)), (o.double() ** 2).sum((0, 1, 2))
+    assert torch.allclose(tot[:, 0], s_ref, rtol=1e-5, atol=1e-2) and torch.allclose(tot[:, 1], q_ref, rtol=1e-5, atol=1e-2)
+    if B == 0:
+        return
+    G = N // B
+    R = B * Hout * Hout
+    gamma, beta = torch.rand(Cn, device="cuda") + 0.5, torch.randn(Cn, device="cuda")
+    outs = [torch.empty(G * Cn, device="cuda") for _ in range(5)]
+    K.bn_fwd_finalize_tiles(part, (B * H * H // 128) * phases, Cn, 1, G, R, Cn, gamma, beta, *outs)
+    refs = [torch.empty(G * Cn, device="cuda") for _ in range(5)]
+    K.bn_fwd_stats(out, G, R, Cn, gamma, beta, *refs)
+    for a, b, nm in zip(outs, refs, ("mean", "invstd", "var_unbiased", "scale", "shift")):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), nm
