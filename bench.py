@@ -178,17 +178,22 @@ def cpu_reference_steps(c, T, B, steps, warmup, threads, skip_prob):
 
 
 def cpu_baseline(c, T, skip_prob, steps, warmup):
-    """Oracle port on the host cores: all cores, and 32 threads when the box has more (the path is ~93k small
-    ATen ops per step, fork/join cost grows with the thread count); the better of the two is the reported value."""
+    """Oracle port on the host cores.  The reference path is ~93k small ATen ops per step; beyond a few
+    dozen threads the per-op fork/join cost dominates: on the 2xx-core GPU hosts an all-core run did not finish ONE
+    T=30,B=16 step in 9 minutes (gpurun_out/r2a, round 2), 32 threads take 3.3 s.  Default = min(cores, 32);
+    P2PVG_CPU_THREADS=a,b,... times each listed thread count and reports the best."""
     B = c["ref_batch"]
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    env = os.environ.get("P2PVG_CPU_THREADS")
+    counts = [int(v) for v in env.split(",")] if env else [min(ncpu, 32)]
     runs = {}
-    for th in sorted({ncpu, min(ncpu, 32)}, reverse=True):
+    for th in counts:
         t = cpu_reference_steps(c, T, B, steps, warmup, th, skip_prob)
         runs[th] = T * B * len(t) / sum(t)
     best = max(runs, key=runs.get)
-    sample = f"{steps} steps of T={T},B={B} of the oracle port (oracle/p2p_oracle.py, Mode A, torch CPU fp32) per thread count; " + \
-             ", ".join(f"{th} threads: {v:.1f} frames/s" for th, v in runs.items())
+    sample = f"{steps} steps of T={T},B={B} of the oracle port (oracle/p2p_oracle.py, Mode A, torch CPU fp32); host has {ncpu} cores; " + \
+             ", ".join(f"{th} threads: {v:.1f} frames/s" for th, v in runs.items()) + \
+             "; more threads are slower on this path (per-op fork/join), see bench.py:cpu_baseline"
     return dict(value=runs[best], unit="frames/s", cores=best, kind="port", sample=sample), runs
 
 
@@ -321,9 +326,21 @@ def main():
 
     log(f'{args.config}: model built (T={T}, B={B}/GPU, world {world}); warm-up')
     # ---- device-timed, batch resident in HBM --------------------------------------------------------
-    nwarm = max(args.warmup, 3) + (6 if args.skip_prob > 0 else 0)   # random skipping: several (T,S) graph signatures to warm
+    nwarm = max(args.warmup, 3)
     for _ in range(nwarm):
         eng.step(x_dev, use_graph=use_graph, return_device=True)
+    if args.skip_prob > 0 and use_graph:
+        # random frame skipping: every (T, executed steps) signature has its own CUDA graph -- warm up until a run of
+        # steps needed no new capture, so that the timed region only replays
+        quiet = 0
+        while quiet < 12 and nwarm < 150:
+            n_before = sum(1 for v in eng._graphs.values() if v != "warm")
+            warm_before = sum(1 for v in eng._graphs.values() if v == "warm")
+            eng.step(x_dev, use_graph=use_graph, return_device=True)
+            nwarm += 1
+            same = (sum(1 for v in eng._graphs.values() if v != "warm") == n_before and
+                    sum(1 for v in eng._graphs.values() if v == "warm") == warm_before == 0)
+            quiet = quiet + 1 if same else 0
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -108,11 +108,14 @@ class TrainEngineVGG(TrainEngine):
     def _imp(self, cin, cout):
         return self.implicit and cin % 64 == 0 and cout % 64 == 0
 
-    def conv3_fwd(self, a, wp, out, N, H, cin, cout, bias=None, addend=None, grp_src=None, ipg=0):
+    def conv3_fwd(self, a, wp, out, N, H, cin, cout, bias=None, addend=None, grp_src=None, ipg=0, stat=None):
+        """stat: stat_buf() workspace -> the BatchNorm statistics of `out` come from the GEMM epilogue (implicit path only)."""
         K = self.K
         if self._imp(cin, cout):
-            K.conv_gemm(3, a, wp, out, N, H, H, cin, cout, bias=bias, addend=addend, grp_src=grp_src, imgs_per_group=ipg)
+            K.conv_gemm(3, a, wp, out, N, H, H, cin, cout, bias=bias, addend=addend, grp_src=grp_src, imgs_per_group=ipg,
+                        stat_partial=stat["buf"] if stat else None)
             return
+        assert stat is None
         ld = _up8(9 * cin)
         col = self.buf("vgg_col", N * H * H * ld)
         K.im2col3(a, col, N, H, H, cin, ld, 1)
@@ -171,8 +174,9 @@ class TrainEngineVGG(TrainEngine):
             M = N * H * H
             raw = self.buf(f"venc_raw{i}_{j}", M * cout)
             y = self.buf(f"venc_y{i}_{j}", M * cout)
-            self.conv3_fwd(a, self._packed[f"enc.{i}.{j}.wp"], raw, N, H, cin, cout, bias=P[pre + ".0.bias"])
-            st = self.bn_forward("venc", f"{i}_{j}", raw, y, T, B * H * H, cout, P[pre + ".1.weight"], P[pre + ".1.bias"], ACT_LRELU)
+            sp = self.stat_buf(f"venc{i}_{j}", M, 1, cout, B * H * H) if self._imp(cin, cout) else None
+            self.conv3_fwd(a, self._packed[f"enc.{i}.{j}.wp"], raw, N, H, cin, cout, bias=P[pre + ".0.bias"], stat=sp)
+            st = self.bn_forward("venc", f"{i}_{j}", raw, y, T, B * H * H, cout, P[pre + ".1.weight"], P[pre + ".1.bias"], ACT_LRELU, tiles=sp)
             self.venc[i].append(dict(inp=a, raw=raw, y=y, st=st, cin=cin, cout=cout, H=H, pre=pre))
             a, C = y, cout
         pooled = self.buf("venc_pool_top", N * 16 * 512)
@@ -228,12 +232,14 @@ class TrainEngineVGG(TrainEngine):
                 skip = self.venc[self.nst - 1 - k][-1]["y"]  # frames are a prefix -> the first nskip frames
                 addS = self.fbuf(f"vdec_addS{k}", nskip * B * H * H * cout)
                 self.conv3_fwd(skip, self._packed[f"dec.{k}.0.S.wp"], addS, nskip * B, H, C, cout, bias=P[pre + ".0.bias"])
-                self.conv3_fwd(a, self._packed[f"dec.{k}.0.D.wp"], raw, N, H, C, cout, addend=addS, grp_src=self.ix["skip_src"], ipg=B)
+                sp = self.stat_buf(f"vdec{k}_{j}", M, 1, cout, B * H * H) if self._imp(C, cout) else None
+                self.conv3_fwd(a, self._packed[f"dec.{k}.0.D.wp"], raw, N, H, C, cout, addend=addS, grp_src=self.ix["skip_src"], ipg=B, stat=sp)
                 rec.update(cin=C, skip=skip)
             else:
-                self.conv3_fwd(a, self._packed[f"dec.{k}.{j}.wp"], raw, N, H, cin, cout, bias=P[pre + ".0.bias"])
+                sp = self.stat_buf(f"vdec{k}_{j}", M, 1, cout, B * H * H) if self._imp(cin, cout) else None
+                self.conv3_fwd(a, self._packed[f"dec.{k}.{j}.wp"], raw, N, H, cin, cout, bias=P[pre + ".0.bias"], stat=sp)
                 rec.update(cin=cin)
-            rec["st"] = self.bn_forward("vdec", f"{k}_{j}", raw, y, G, B * H * H, cout, P[pre + ".1.weight"], P[pre + ".1.bias"], ACT_LRELU)
+            rec["st"] = self.bn_forward("vdec", f"{k}_{j}", raw, y, G, B * H * H, cout, P[pre + ".1.weight"], P[pre + ".1.bias"], ACT_LRELU, tiles=sp)
             self.vdec[k].append(rec)
             a, C = y, cout
         # ConvTranspose2d(64, nc, 3, 1, 1): [pix,64] x [64, 9*nc] GEMM, then the 9-tap gather; the Sigmoid lives in the loss kernel
