@@ -60,7 +60,7 @@ __device__ __forceinline__ void pix_block(int pb, int P, int H, int W, int bh, i
   }
 }
 
-template <int KIND, int BN>
+template <int KIND, int BN, bool STAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv, int c_bf16,
                  long long ldc, Geom g, int accumulate, const float* __restrict__ bias, const float* __restrict__ addend,
@@ -237,8 +237,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __shared__ float bias_s[2 * BN];
     // BatchNorm forward statistics fused into the epilogue: per-warp column sums (sum y, sum y^2) of the tile, double-
     // buffered by accumulator so that tile t+1 may write while the sums of tile t are still being combined
-    __shared__ float2 stat_s[(KIND == 1) ? 1 : 2 * 4 * BN];
-    const bool do_stat = (KIND != 1) && stat_partial != nullptr;
+    __shared__ float2 stat_s[STAT ? 2 * 4 * BN : 1];
+    constexpr bool do_stat = STAT;   // a separate instantiation: the statistics cost ~50 registers in this epilogue
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
       const int ph = (KIND == 2) ? (t & 3) : 0;
@@ -339,7 +339,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[4 * j] += x4.x; f[4 * j + 1] += x4.y; f[4 * j + 2] += x4.z; f[4 * j + 3] += x4.w;
             }
           }
-          if (KIND != 1 && do_stat) {
+          if (STAT) {
             // statistics of the tensor AS STORED (bf16-rounded when the output is bf16); all 32 lanes take part
             float s1[32], s2[32];
 #pragma unroll
@@ -393,7 +393,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if (KIND != 1 && do_stat) {
+      if (STAT) {
         // combine the four warps' column sums in a fixed order (deterministic) -> one partial row per (pixel tile, phase)
         epi_bar_sync();
         float2* dst = stat_partial + ((long long)mt * phases + ph) * g.Ntot + n0;
@@ -434,7 +434,7 @@ std::once_flag g_once2;
 int g_sms = 148;
 int g_k1_wide_max = 1 << 30;  // kind 1: 256-wide tiles while there are at most this many 128-wide output tiles (P2PVG_K1_WIDE_MAX)
 int g_bn256 = 1;  // P2PVG_CONV_BN256=0 keeps the 128-wide tiles (A/B comparison)
-int g_attr[3][3] = {};
+int g_attr[2][3][3] = {};
 
 void resolve2() {
   int dev = 0, sms = 0;
@@ -493,12 +493,25 @@ bool box_for(int P, int H, int W, int& bh, int& bn) {
   return bh * 2 <= 256 && W * 2 <= 256 && bn <= 256;
 }
 
+template <int KIND, int BN, bool STAT>
+int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, const Geom& g, int accumulate,
+             const float* bias, const float* addend, const int* grp_src, float* partial, int splits, int kb_per_split, cudaStream_t st,
+             float2* stat_partial);
+
 template <int KIND, int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, const Geom& g, int accumulate,
            const float* bias, const float* addend, const int* grp_src, float* partial, int splits, int kb_per_split, cudaStream_t st,
            float2* stat_partial = nullptr) {
-  auto kern = conv_gemm_kernel<KIND, BN>;
-  int& done = g_attr[KIND][BN == 256 ? 2 : BN == 128];
+  if (KIND != 1 && stat_partial != nullptr) return launch_t<KIND, BN, (KIND != 1)>(ta, tb, C, c_dtype, ldc, g, accumulate, bias, addend, grp_src, partial, splits, kb_per_split, st, stat_partial);
+  return launch_t<KIND, BN, false>(ta, tb, C, c_dtype, ldc, g, accumulate, bias, addend, grp_src, partial, splits, kb_per_split, st, nullptr);
+}
+
+template <int KIND, int BN, bool STAT>
+int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, const Geom& g, int accumulate,
+             const float* bias, const float* addend, const int* grp_src, float* partial, int splits, int kb_per_split, cudaStream_t st,
+             float2* stat_partial) {
+  auto kern = conv_gemm_kernel<KIND, BN, STAT>;
+  int& done = g_attr[STAT][KIND][BN == 256 ? 2 : BN == 128];
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) {

@@ -86,10 +86,11 @@ class StepPlan:
 
 
 class ParamArena:
-    """Flat fp32 storage of one module's parameters (+ grads + Adam moments) with named views, so the
-    optimiser is one kernel and the data-parallel gradient exchange one all-reduce per module."""
+    """Flat fp32 storage of one module's parameters (+ grads + Adam moments) with named views, so the optimiser is one
+    kernel per module.  The arenas of all modules are carved out of ONE allocation per kind (`pool`), laid out in the order
+    the gradients become final, so the data-parallel exchange is one all-reduce per contiguous bucket."""
 
-    def __init__(self, named_tensors, device):
+    def __init__(self, named_tensors, device, pool=None):
         self.names, self.shapes, self.offsets = [], {}, {}
         off = 0
         for k, v in named_tensors.items():
@@ -98,10 +99,13 @@ class ParamArena:
             self.offsets[k] = off
             off += (v.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
         self.numel = off
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
-        self.m = torch.zeros(off, dtype=torch.float32, device=device)
-        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        if pool is None:
+            self.flat, self.grad, self.m, self.v = (torch.zeros(off, dtype=torch.float32, device=device) for _ in range(4))
+            self.base = 0
+        else:
+            self.base = pool["used"]
+            pool["used"] += (off + 63) // 64 * 64
+            self.flat, self.grad, self.m, self.v = (pool[nm][self.base:self.base + off] for nm in ("flat", "grad", "m", "v"))
         self.step_t = torch.zeros(1, dtype=torch.int32, device=device)
         self.p, self.g = {}, {}
         for k, v in named_tensors.items():
@@ -110,9 +114,19 @@ class ParamArena:
             self.g[k] = self.grad[o:o + n].view(self.shapes[k])
             self.p[k].copy_(v.detach().to(device=device, dtype=torch.float32))
 
+    @staticmethod
+    def padded(named_tensors):
+        n = sum((v.numel() + 3) // 4 * 4 for v in named_tensors.values())
+        return (n + 63) // 64 * 64
+
     def moment_views(self, k):
         o, n = self.offsets[k], int(np.prod(self.shapes[k])) if self.shapes[k] else 1
         return self.m[o:o + n].view(self.shapes[k]), self.v[o:o + n].view(self.shapes[k])
+
+
+# arena order = order in which the gradients of Mode A become final: backward #1 finishes decoder, frame predictor and
+# posterior first (one exchange bucket), then the encoder, then backward #2 the prior
+ARENA_ORDER = ("decoder", "frame_predictor", "posterior", "encoder", "prior")
 
 
 def is_param_key(key):
@@ -144,9 +158,11 @@ class TrainEngine:
         else:
             self.frame_elems = 51  # h36m pose: 17 joints x 3
         self.arena, self.buffers = {}, {}
-        for m in ("frame_predictor", "posterior", "prior", "encoder", "decoder"):
-            params = OrderedDict((k, v) for k, v in state[m].items() if is_param_key(k))
-            self.arena[m] = ParamArena(params, self.dev)
+        params = {m: OrderedDict((k, v) for k, v in state[m].items() if is_param_key(k)) for m in ARENA_ORDER}
+        total = sum(ParamArena.padded(params[m]) for m in ARENA_ORDER)
+        self.pool = dict(used=0, **{nm: torch.zeros(total, dtype=torch.float32, device=self.dev) for nm in ("flat", "grad", "m", "v")})
+        for m in ARENA_ORDER:
+            self.arena[m] = ParamArena(params[m], self.dev, pool=self.pool)
             self.buffers[m] = {k: v.detach().clone().to(self.dev) for k, v in state[m].items() if not is_param_key(k)}
         self._bufs = {}
         self._buf_gen = 0
@@ -172,43 +188,63 @@ class TrainEngine:
         # BatchNorm forward statistics come out of the producing implicit GEMM's epilogue (per-tile column sums) instead of a
         # separate pass over the stored tensor; P2PVG_BN_FUSE=0 keeps the stand-alone statistics kernel (A/B comparison)
         self.fuse_stats = self.implicit and os.environ.get("P2PVG_BN_FUSE", "1") != "0"
+        # ... but only where the tile's MMA time hides the extra epilogue work: reduction length x tile width of the GEMM must
+        # reach this many MACs per output row (measured: low-K tiles are epilogue-bound and get slower)
+        self.fuse_stats_min = int(os.environ.get("P2PVG_BN_FUSE_MIN", str(2048 * 128)))
         self.overlap = getattr(kernels, "name", "") == "cuda" and os.environ.get("P2PVG_OVERLAP", "0") == "1"
-        self.side = None
-        self._side_dirty = False
+        # independent chains of small kernels (the three LSTMs, backward #2) run on side streams inside the captured graph
+        self.concurrent = getattr(kernels, "name", "") == "cuda" and act_dtype == torch.bfloat16 and os.environ.get("P2PVG_CONCURRENT", "1") != "0" \
+            and os.environ.get("P2PVG_LSTM_CLUSTER", "1") != "0"   # (the cooperative-grid scans must not share the GPU with a second grid-barrier kernel)
+        self.streams, self._dirty, self._serial = {}, set(), False
         self.last_plan = None
         self.phase_events = None
 
-    # ------------------------------------------------------------------ side stream
-    def fork(self):
-        """Context manager: kernels enqueued inside run on the side stream, after everything enqueued on the main stream so far."""
+    # ------------------------------------------------------------------ side streams ("lanes")
+    # lane 0 = the caller's stream.  lane 1: the prior LSTM while the posterior runs on lane 0 (independent recurrences until
+    # z); lane 2: weight-gradient work (never on the critical path); lane 3: backward #2 (CPC chain + prior BPTT, independent
+    # of the encoder backward).  Every lane has its own workspaces (K.lane).  All of it is captured into the one CUDA graph.
+    LANE_PRIOR, LANE_WGRAD, LANE_BWD2 = 1, 2, 3
+
+    def fork(self, lane=2, heavy=False):
+        """Context manager: kernels enqueued inside run on side stream `lane`, after everything enqueued on the current
+        stream so far.  heavy=True marks persistent all-SM GEMMs, which gain little from a co-resident kernel: those forks
+        are only taken with P2PVG_OVERLAP=1.  Forks are only taken from lane 0 (no nesting) and never while phases are
+        being timed."""
         import contextlib
-        if not self.overlap or self.phase_events is not None:
+        on = self.overlap if heavy else self.concurrent
+        if not on or self.phase_events is not None or self._serial or self.K.lane != 0:
             return contextlib.nullcontext()
-        if self.side is None:
-            self.side = torch.cuda.Stream(device=self.dev)
+        st = self.streams.get(lane)
+        if st is None:
+            st = self.streams[lane] = torch.cuda.Stream(device=self.dev)
         ev = torch.cuda.Event()
-        ev.record()
-        self.side.wait_event(ev)
-        self._side_dirty = True
+        ev.record(torch.cuda.current_stream(self.dev))
+        st.wait_event(ev)
+        self._dirty.add(lane)
         eng = self
 
         @contextlib.contextmanager
         def ctx():
-            eng.K.lane = 1
+            eng.K.lane = lane
             try:
-                with torch.cuda.stream(eng.side):
+                with torch.cuda.stream(st):
                     yield
             finally:
                 eng.K.lane = 0
         return ctx()
 
-    def join(self):
-        """The main stream waits for everything enqueued on the side stream."""
-        if self._side_dirty:
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-            torch.cuda.current_stream(self.dev).wait_event(ev)
-            self._side_dirty = False
+    def join(self, *lanes):
+        """The current stream waits for everything enqueued on the given side lanes (default: all)."""
+        for lane in (lanes or tuple(self._dirty)):
+            if lane in self._dirty:
+                ev = torch.cuda.Event()
+                ev.record(self.streams[lane])
+                torch.cuda.current_stream(self.dev).wait_event(ev)
+                self._dirty.discard(lane)
+
+    def lbuf(self, name, numel, dtype=None):
+        """Scratch buffer private to the lane that is enqueueing (concurrent lanes must not share scratch)."""
+        return self.buf(f"{name}@{self.K.lane}" if self.K.lane else name, numel, dtype)
 
     # ------------------------------------------------------------------ memory
     def buf(self, name, numel, dtype=None):
@@ -320,8 +356,8 @@ class TrainEngine:
         K = self.K
         ldx = ldx or in_dim
         if self.tc_lstm and out_dim % 8 == 0 and ldx % 8 == 0:
-            a = self.buf("wg_castA", rows * out_dim, torch.bfloat16)
-            b = self.buf("wg_castB", rows * ldx, torch.bfloat16)
+            a = self.lbuf("wg_castA", rows * out_dim, torch.bfloat16)
+            b = self.lbuf("wg_castB", rows * ldx, torch.bfloat16)
             K.permute4(dY, a, (rows * out_dim, 1, 1, 1), (1, 0, 0, 0))
             K.permute4(X, b, (rows * ldx, 1, 1, 1), (1, 0, 0, 0))
             K.gemm(a, b, gW, out_dim, in_dim, rows, a_mn=True, b_mn=True, lda=out_dim, ldb=ldx)
@@ -419,46 +455,68 @@ class TrainEngine:
 
     def _run_inner(self, x, plan):
         self._mark("start")
-        for name, fn in self.phases(x, plan):
-            fn()
+        for name, fn, lane in self.phases(x, plan):
+            if lane:
+                with self.fork(lane):
+                    fn()
+            else:
+                fn()
             self._mark(name)
+        self.join()
 
     def phases(self, x, plan):
-        """The step as an ordered list of (name, thunk).  _run executes them back to back; time_phases() captures each
-        one into its own CUDA graph to time it without launch gaps (bench.py: LSTM-phase roofline)."""
-        non_prior = ("frame_predictor", "posterior", "encoder", "decoder")
+        """The step as an ordered list of (name, thunk, lane).  _run executes them in order -- a phase with lane != 0 is
+        enqueued on that side stream and runs concurrently with the phases after it until they join; time_phases()
+        captures each one alone into its own CUDA graph (bench.py: per-phase times, LSTM-phase roofline).
 
-        def adam4():
-            self.adam(non_prior)
-            if self.mode == "A":   # backward #2 runs through the UPDATED decoder / predictor weights (SURVEY.md §0.5)
-                self.pack_weights(("decoder",))
-                self.pack_lstm_weights()
+        Mode A (the reference's two-phase update): backward #2 (CPC chain + prior BPTT) reads the UPDATED
+        decoder / frame-predictor weights and nothing of the encoder's, so those three modules are stepped as soon as
+        their gradients exist and backward #2 runs beside the encoder backward."""
+        def adam_of(mods, repack=False):
+            def f():
+                self.join()
+                self.adam(mods)
+                if repack:   # backward #2 runs through the UPDATED decoder / predictor weights
+                    self.pack_weights(("decoder",))
+                    self.pack_lstm_weights()
+            return f
 
-        ph = [("pack", lambda: (self.pack_weights(), self.pack_lstm_weights())),
-              ("encode_fwd", lambda: self.encode(x, plan)),
-              ("lstm_fwd", lambda: self.recurrent_fwd(plan)),
-              ("decode_fwd", lambda: (self.decode(plan), self.losses_fwd(plan))),
-              ("decoder_bwd", lambda: self.backward_decoder(plan)),
-              ("lstm_bwd", lambda: self.backward_recurrent(plan)),
-              ("encoder_bwd", lambda: self.encoder_backward(plan))]
-        if self.mode == "A":
-            ph += [("adam4+repack", adam4), ("prior_bwd", lambda: self.backward_prior(plan))]
+        ph = [("pack", lambda: (self.pack_weights(), self.pack_lstm_weights()), 0),
+              ("encode_fwd", lambda: self.encode(x, plan), 0),
+              ("lstm_fwd", lambda: self.recurrent_fwd(plan), 0),
+              ("decode_fwd", lambda: (self.decode(plan), self.losses_fwd(plan)), 0),
+              ("decoder_bwd", lambda: self.backward_decoder(plan), 0),
+              ("lstm_bwd", lambda: self.backward_recurrent(plan), 0)]
+        if self.mode == "A" and self.dist is not None and self.concurrent and not self._serial:
+            # data parallel: the exchange of the first bucket (decoder + predictor + posterior), their Adam step, the re-pack
+            # and backward #2 form ONE chain on the side lane -- the all-reduce overlaps the encoder backward
+            a3 = adam_of(("frame_predictor", "posterior", "decoder"), repack=True)
+            ph += [("allreduce+adam3+repack+prior_bwd", lambda: (a3(), self.backward_prior(plan)), self.LANE_BWD2),
+                   ("encoder_bwd", lambda: self.encoder_backward(plan), 0),
+                   ("adam_enc+prior", adam_of(("encoder", "prior")), 0)]
+        elif self.mode == "A":
+            ph += [("adam3+repack", adam_of(("frame_predictor", "posterior", "decoder"), repack=True), 0),
+                   ("prior_bwd", lambda: self.backward_prior(plan), self.LANE_BWD2),
+                   ("encoder_bwd", lambda: self.encoder_backward(plan), 0),
+                   ("adam_enc+prior", adam_of(("encoder", "prior")), 0)]
         else:
-            ph += [("prior_bwd", lambda: self.backward_prior(plan)), ("adam4", adam4)]
-        ph.append(("adam_prior", lambda: self.adam(("prior",))))
+            ph += [("prior_bwd", lambda: self.backward_prior(plan), self.LANE_BWD2),
+                   ("encoder_bwd", lambda: self.encoder_backward(plan), 0),
+                   ("adam5", adam_of(("frame_predictor", "posterior", "encoder", "decoder", "prior")), 0)]
         return ph
 
     def time_phases(self, x, reps=5):
-        """Device time (ms) of every phase of a step on batch `x`, each phase captured into its own CUDA graph and
-        replayed `reps` times between CUDA events.  Leaves the optimiser / BatchNorm state advanced: measurement only.
-        No collectives (single-rank measurement)."""
+        """Device time (ms) of every phase of a step on batch `x`, each phase captured ALONE (no concurrent lanes) into its
+        own CUDA graph and replayed `reps` times between CUDA events.  Leaves the optimiser / BatchNorm state advanced:
+        measurement only.  No collectives (single-rank measurement)."""
         plan = self.last_plan
         saved, self.dist = self.dist, None
         out = {}
         try:
             self._run(x, plan)   # eager: every buffer exists, activations of this batch are in place
             torch.cuda.synchronize(self.dev)
-            for name, fn in self.phases(x, plan):
+            self._serial = True
+            for name, fn, _ in self.phases(x, plan):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     fn()
@@ -472,6 +530,7 @@ class TrainEngine:
                 out[name] = e0.elapsed_time(e1) / reps
                 del g
         finally:
+            self._serial = False
             self.dist = saved
             self._graphs.clear()
         return out
@@ -510,7 +569,7 @@ class TrainEngine:
             thin = self.thin and cin <= 4
             sp = None
             if imp:
-                sp = self.stat_buf(f"enc{l}", M, 1, cout, B * Ho * Ho)
+                sp = self.stat_buf(f"enc{l}", M, 1, cout, B * Ho * Ho, kred=16 * cin)
                 K.conv_gemm(0, a, self._packed[f"enc{l}"], raw, N, Ho, Ho, cin, cout, bias=P[cn + ".bias"],
                             stat_partial=sp["buf"] if sp else None)
             elif thin:  # 1/3-channel input: direct HBM-bound kernel on the fp32 master weights
@@ -548,10 +607,12 @@ class TrainEngine:
                      st["C"], BN_MOMENTUM)
             Bf[bn + ".num_batches_tracked"] += ncalls
 
-    def stat_buf(self, tag, rows, phases, C, rows_per_group):
+    def stat_buf(self, tag, rows, phases, C, rows_per_group, kred=1 << 30):
         """Workspace for the per-tile BatchNorm statistics of a GEMM epilogue, or None when the fusion does not apply
-        (a 128-row tile must not straddle two BatchNorm groups).  rows: GEMM rows (per phase)."""
-        if not self.fuse_stats or rows_per_group % 128 != 0 or rows % 128 != 0:
+        (a 128-row tile must not straddle two BatchNorm groups) or does not pay (kred = reduction length of one tile: short
+        reductions leave the epilogue no MMA time to hide behind).  rows: GEMM rows (per phase)."""
+        bn_tile = 256 if C % 256 == 0 else 128 if C > 64 else 64
+        if not self.fuse_stats or rows_per_group % 128 != 0 or rows % 128 != 0 or kred * bn_tile < self.fuse_stats_min:
             return None
         buf = self.fbuf(f"bnpart_{tag}", (rows // 128) * phases * C * 2)
         return dict(buf=buf, parts_per_group=(rows_per_group // 128) * phases, ldp=C, fold=1)
@@ -604,7 +665,7 @@ class TrainEngine:
             K.gemm(inp, P[f"lstm.{l}.weight_ih"], Pre, rows, 4 * R, R, bias=P[f"lstm.{l}.bias_ih"])
             whh, bhh = P[f"lstm.{l}.weight_hh"], P[f"lstm.{l}.bias_hh"]
             if self.fused_scan:
-                ctr = self.buf("scan_counter", 4, torch.int32)
+                ctr = self.lbuf("scan_counter", 4, torch.int32)
                 ctr.zero_()
                 K.lstm_scan_fwd(Pre, whh, bhh, gates, hs, cs, steps, B, R, ctr, tf32=self.tc_lstm)
             for s in range(0 if not self.fused_scan else steps, steps):
@@ -629,7 +690,8 @@ class TrainEngine:
         K.build_concat(Xprior, H, ix["in_idx"], g, H, ix["glob_idx"], g, self.tuc, self.dt, S, B, ld=lw)
         self.sv = {}
         heads = {}
-        for m, X in (("posterior", Xpost), ("prior", Xprior)):
+
+        def gaussian(m, X):
             sv = self.lstm_forward(m, X, S, win)
             P = self.arena[m].p
             mu = self.fbuf(f"{m}_mu", S * B * z)
@@ -638,6 +700,12 @@ class TrainEngine:
             K.gemm(sv["top"], P["logvar_net.weight"], lv, S * B, z, R, bias=P["logvar_net.bias"])
             heads[m] = (mu, lv)
             self.sv[m] = sv
+
+        # posterior and prior are independent recurrences until z (models/p2p_model.py:244-245): two lanes
+        with self.fork(self.LANE_PRIOR):
+            gaussian("prior", Xprior)
+        gaussian("posterior", Xpost)
+        self.join(self.LANE_PRIOR)
         self.mu, self.lv = heads["posterior"]
         self.mu_p, self.lv_p = heads["prior"]
         n = S * B * z
@@ -698,7 +766,7 @@ class TrainEngine:
                 # skip half once per distinct source frame (fp32, bias folded in), added in the epilogue of the main GEMM
                 addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
                 K.conv_gemm(2, skip, wS, addS, nskip * B, Hi, Hi, cd, cout, bias=P[cn + ".bias"])
-                sp = self.stat_buf(f"dec{k}", Md, 4, cout, B * Hi * Hi) if k < n - 1 else None
+                sp = self.stat_buf(f"dec{k}", Md, 4, cout, B * Hi * Hi, kred=4 * cd) if k < n - 1 else None
                 K.conv_gemm(2, d, wD, raw, N, Hi, Hi, cd, cout, addend=addS, grp_src=self.ix["skip_src"], imgs_per_group=B,
                             stat_partial=sp["buf"] if sp else None)
             elif self.thin and cout <= 3 and cd % 8 == 0:
@@ -782,7 +850,7 @@ class TrainEngine:
                 # data gradient = stride-2 conv of dy; weight gradients gather dy by filter tap; the skip half works
                 # on dy summed over the calls that share a skip frame (conv is linear) -- no col buffers at all.
                 # Only the data gradient is on the critical path: everything else goes to the side stream.
-                with self.fork():
+                with self.fork(self.LANE_WGRAD, heavy=True):
                     if want_wgrad:
                         K.conv_gemm(1, x_in, dy, gw[:cd * 16 * cout], N, Hi, Hi, 0, cout, Cm=cd)
                     if want_skip:
@@ -889,7 +957,7 @@ class TrainEngine:
             whh = P[f"lstm.{l}.weight_hh"]
             dc_next = None
             if self.fused_scan:
-                ctr = self.buf("scan_counter", 4, torch.int32)
+                ctr = self.lbuf("scan_counter", 4, torch.int32)
                 ctr.zero_()
                 K.lstm_scan_bwd(dH, whh, lay["gates"], lay["cs"], dG, steps, B, R, ctr, tf32=self.tc_lstm)
             for s in (range(steps - 1, -1, -1) if not self.fused_scan else ()):
@@ -904,18 +972,20 @@ class TrainEngine:
                                      dG[s * B * 4 * R:(s + 1) * B * 4 * R], dc_prev, B, R)
                 dc_next = dc_prev
             if want_wgrad:
-                self.lin_wgrad(dG, lay["hs"], A.g[f"lstm.{l}.weight_hh"], rows, 4 * R, R)
-                self.lin_wgrad(dG, lay["inp"], A.g[f"lstm.{l}.weight_ih"], rows, 4 * R, R)
-                K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_ih"])
-                K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_hh"])
+                with self.fork(self.LANE_WGRAD):   # off the critical path: nothing below reads a weight gradient
+                    self.lin_wgrad(dG, lay["hs"], A.g[f"lstm.{l}.weight_hh"], rows, 4 * R, R)
+                    self.lin_wgrad(dG, lay["inp"], A.g[f"lstm.{l}.weight_ih"], rows, 4 * R, R)
+                    K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_ih"])
+                    K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_hh"])
             dIn = self.fbuf(f"{m}_dIn{l}", rows * R)
             self.lin_dinput(m, f"lstm.{l}.weight_ih", dG, dIn, rows, 4 * R, R)
             dH = dIn
         dE = dH
         in_dim = sv["in_dim"]
         if want_wgrad:
-            self.lin_wgrad(dE, sv["X"], A.g["embed.weight"], rows, R, in_dim, ldx=sv["ldx"])
-            K.colsum(dE, rows, R, R, A.g["embed.bias"])
+            with self.fork(self.LANE_WGRAD):
+                self.lin_wgrad(dE, sv["X"], A.g["embed.weight"], rows, R, in_dim, ldx=sv["ldx"])
+                K.colsum(dE, rows, R, R, A.g["embed.bias"])
         if want_dx:
             dX = dx_out if dx_out is not None else self.fbuf(f"{m}_dX", rows * in_dim)
             self.lin_dinput(m, "embed.weight", dE, dX, rows, R, in_dim)
@@ -977,10 +1047,12 @@ class TrainEngine:
         K.reparam_kl_bwd(self.mu, self.lv, self.mu_p, self.lv_p, self.eps_post, self.eps_prior, dz, None,
                          float(opt["beta"]) / float(opt["batch_size"]), dmu, dlv, dmu_p, dlv_p, n)
         win = 2 * g + 2
+        with self.fork(self.LANE_PRIOR):
+            dtop_p = self.gaussian_heads_backward("prior", dmu_p, dlv_p, S, want_wgrad=False)
+            dXprior = self.lstm_backward("prior", dtop_p, S, want_wgrad=False, want_dx=True)
         dtop = self.gaussian_heads_backward("posterior", dmu, dlv, S, want_wgrad=True)
         dXpost = self.lstm_backward("posterior", dtop, S, want_wgrad=True, want_dx=True)
-        dtop = self.gaussian_heads_backward("prior", dmu_p, dlv_p, S, want_wgrad=False)
-        dXprior = self.lstm_backward("prior", dtop, S, want_wgrad=False, want_dx=True)
+        self.join(self.LANE_PRIOR)
         # latent gradients -> dH[T,B,g]
         ix = self.ix
         K.gather_add_cols(self.dH, dXpost, ix["tgt_idx"], S, T, B, g, win, 0)
@@ -994,7 +1066,7 @@ class TrainEngine:
         A = self.arena["encoder"]
         N = T * B
         nskip = plan.nskip
-        self.join()   # the skip gradients of the decoder come from the side stream
+        self.join(self.LANE_WGRAD)   # the skip gradients of the decoder come from the side stream
         if self.adt == torch.float32:
             dy = self.dH
         else:
@@ -1027,7 +1099,7 @@ class TrainEngine:
             A.g[cn + ".bias"].zero_()
             gw = self.fbuf(f"gwp_enc{l}", cout * 16 * cin)
             if rec["imp"]:
-                with self.fork():   # off the critical path
+                with self.fork(self.LANE_WGRAD, heavy=True):   # off the critical path
                     K.conv_gemm(1, gy, rec["inp"], gw, N, Ho, Ho, 0, cin, Cm=cout)
                     K.transpose_batched(gw, A.g[cn + ".weight"], cout, 16, cin)   # [co][tap][ci] -> [co][ci][tap]
             else:
@@ -1085,16 +1157,39 @@ class TrainEngine:
         self.lstm_backward("prior", dtop, S, want_wgrad=True, want_dx=False)
 
     # -- optimiser --------------------------------------------------------------------------
+    def grad_bucket(self, modules):
+        """The contiguous slice of the pooled gradient arena that holds `modules` (they must be neighbours in ARENA_ORDER)."""
+        idx = sorted(ARENA_ORDER.index(m) for m in modules)
+        assert idx == list(range(idx[0], idx[-1] + 1)), f"{modules} are not contiguous in the arena"
+        first, last = self.arena[ARENA_ORDER[idx[0]]], self.arena[ARENA_ORDER[idx[-1]]]
+        return self.pool["grad"][first.base:last.base + last.numel]
+
+    def allreduce(self, modules):
+        """Data parallel: replicas hold batch shards; average the gradients of `modules` over NVLink -- ONE ncclAllReduce
+        (AVG, no separate scaling pass) per contiguous bucket of the pooled arena."""
+        dist, group, world = self.dist
+        mods = sorted(modules, key=ARENA_ORDER.index)
+        runs, cur = [], [mods[0]]
+        for m in mods[1:]:
+            if ARENA_ORDER.index(m) == ARENA_ORDER.index(cur[-1]) + 1:
+                cur.append(m)
+            else:
+                runs.append(cur)
+                cur = [m]
+        runs.append(cur)
+        for run in runs:
+            buf = self.grad_bucket(run)
+            if buf.is_cuda:
+                dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)
+            else:   # gloo (CPU tests) has no AVG
+                dist.all_reduce(buf, group=group)
+                self.K.scale(buf, buf.numel(), 1.0 / world)
+
     def adam(self, modules):
         opt = self.opt
-        self.join()   # weight gradients produced on the side stream
+        self.join()   # weight gradients / side chains produced on other lanes
         if self.dist is not None:
-            # data parallel: replicas hold batch shards; average the flat gradient arenas over NVLink (NCCL)
-            dist, group, world = self.dist
-            for m in modules:
-                A = self.arena[m]
-                dist.all_reduce(A.grad, group=group)
-                self.K.scale(A.grad, A.numel, 1.0 / world)
+            self.allreduce(modules)
         for m in modules:
             A = self.arena[m]
             A.step_t += 1

@@ -174,7 +174,7 @@ class TrainEngineVGG(TrainEngine):
             M = N * H * H
             raw = self.buf(f"venc_raw{i}_{j}", M * cout)
             y = self.buf(f"venc_y{i}_{j}", M * cout)
-            sp = self.stat_buf(f"venc{i}_{j}", M, 1, cout, B * H * H) if self._imp(cin, cout) else None
+            sp = self.stat_buf(f"venc{i}_{j}", M, 1, cout, B * H * H, kred=9 * cin) if self._imp(cin, cout) else None
             self.conv3_fwd(a, self._packed[f"enc.{i}.{j}.wp"], raw, N, H, cin, cout, bias=P[pre + ".0.bias"], stat=sp)
             st = self.bn_forward("venc", f"{i}_{j}", raw, y, T, B * H * H, cout, P[pre + ".1.weight"], P[pre + ".1.bias"], ACT_LRELU, tiles=sp)
             self.venc[i].append(dict(inp=a, raw=raw, y=y, st=st, cin=cin, cout=cout, H=H, pre=pre))
@@ -232,11 +232,11 @@ class TrainEngineVGG(TrainEngine):
                 skip = self.venc[self.nst - 1 - k][-1]["y"]  # frames are a prefix -> the first nskip frames
                 addS = self.fbuf(f"vdec_addS{k}", nskip * B * H * H * cout)
                 self.conv3_fwd(skip, self._packed[f"dec.{k}.0.S.wp"], addS, nskip * B, H, C, cout, bias=P[pre + ".0.bias"])
-                sp = self.stat_buf(f"vdec{k}_{j}", M, 1, cout, B * H * H) if self._imp(C, cout) else None
+                sp = self.stat_buf(f"vdec{k}_{j}", M, 1, cout, B * H * H, kred=9 * C) if self._imp(C, cout) else None
                 self.conv3_fwd(a, self._packed[f"dec.{k}.0.D.wp"], raw, N, H, C, cout, addend=addS, grp_src=self.ix["skip_src"], ipg=B, stat=sp)
                 rec.update(cin=C, skip=skip)
             else:
-                sp = self.stat_buf(f"vdec{k}_{j}", M, 1, cout, B * H * H) if self._imp(cin, cout) else None
+                sp = self.stat_buf(f"vdec{k}_{j}", M, 1, cout, B * H * H, kred=9 * cin) if self._imp(cin, cout) else None
                 self.conv3_fwd(a, self._packed[f"dec.{k}.{j}.wp"], raw, N, H, cin, cout, bias=P[pre + ".0.bias"], stat=sp)
                 rec.update(cin=cin)
             rec["st"] = self.bn_forward("vdec", f"{k}_{j}", raw, y, G, B * H * H, cout, P[pre + ".1.weight"], P[pre + ".1.bias"], ACT_LRELU, tiles=sp)
