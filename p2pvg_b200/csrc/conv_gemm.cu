@@ -413,6 +413,257 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// kind 2 with the FOUR output-parity phases fused into one tile (ConvTranspose2d 4x4 / s2 / p1 forward, Conv2d data gradient).
+// A tile = 128 small-map pixels x (4 phases x 64 output channels) = 128 x 256 accumulator columns; column block p = 2a + b
+// is output parity (a, b).  out[2y+a, 2x+b] = sum over the 2x2 taps of phase (a, b) of x[y+dy, x+dx] . W[ky, kx]:
+// the nine shifted pixel boxes (dy, dx) in {-1,0,1}^2 are each fetched ONCE per channel chunk and multiplied (N = 64
+// tcgen05.mma) against the weight taps of every phase that uses the shift: (0,0) serves 4 phases, an edge shift 2, a corner
+// shift 1 -- 16 (shift, phase) products per chunk like the phase-by-phase kernel, but 9 A tiles instead of 16: 123 FLOP per
+// shared-memory fill byte instead of 43 (64 output channels) / 65 (128), i.e. off the L2 -> SM operand-fill limit that held
+// those layers at 520 - 660 TFLOP/s.  Output channels beyond 64 are further tiles (n-tile nt = channels
+// [64 nt, 64 nt + 64)).  Epilogue as in conv_gemm_kernel (bias, fp32 skip addend, bf16 / fp32 store, optional BatchNorm
+// statistics), one 64-column round per phase.
+__device__ __forceinline__ bool phase_uses(int a, int d) { return d == 0 || (d < 0 ? a == 0 : a == 1); }
+__device__ __forceinline__ int phase_tap(int a, int d) { return d == 0 ? a + 1 : (a ? 0 : 3); }
+
+template <bool STAT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv, int c_bf16,
+              long long ldc, Geom g, const float* __restrict__ bias, const float* __restrict__ addend, const int* __restrict__ grp_src,
+              float2* __restrict__ stat_partial) {
+  constexpr int BN = 256;
+  using C_ = Cfg<BN>;
+  constexpr int UMMA_K = 16;
+  constexpr int B_TILE_BYTES = 64 * 128;   // 64 reduction channels x 64 output channels (MN-major)
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C_::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C_::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M, tiles_n = g.Cn / 64;
+  const int num_tiles = tiles_m * tiles_n;
+  const int cchunks = g.Ck / 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C_::STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: one stage = one shifted pixel box + the weight taps of the phases using it
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = (tiles_n == 1) ? t : t / tiles_n, nt = (tiles_n == 1) ? 0 : t - mt * tiles_n;
+        int pn0, py0;
+        pix_block(mt, 128, g.H, g.W, g.bh128, g.bn128, pn0, py0);
+        for (int cc = 0; cc < cchunks; cc++) {
+          const int c0 = cc * 64;
+#pragma unroll
+          for (int sh = 0; sh < 9; sh++, it++) {
+            const int dy = sh / 3 - 1, dx = sh % 3 - 1;
+            const int nb = (dy == 0 ? 2 : 1) * (dx == 0 ? 2 : 1);
+            const int s = it % C_::STAGES;
+            const uint32_t par = (it / C_::STAGES) & 1;
+            mbar_wait(&empty_bar[s], par ^ 1);
+            uint8_t* sa = smem + s * C_::STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + nb * B_TILE_BYTES);
+            tma_load_4d(&tmA, &full_bar[s], sa, c0, dx, py0 + dy, pn0);
+            int j = 0;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+              const int a = p >> 1, b = p & 1;
+              if (!phase_uses(a, dy) || !phase_uses(b, dx)) continue;
+              const int ky = phase_tap(a, dy), kx = phase_tap(b, dx);
+              tma_load_2d(&tmB, &full_bar[s], sb + j * B_TILE_BYTES, (ky * 4 + kx) * g.Cn + nt * 64, c0);
+              j++;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t da0 = make_desc(smem0, 0, 1024);
+      const uint64_t db0 = make_desc(smem0 + A_STAGE_BYTES, 64 * 128, 1024);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
+        const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+        tcgen05_fence_after();
+        uint32_t started = 0;   // bit p: phase p's columns hold a partial sum of this tile
+        for (int cc = 0; cc < cchunks; cc++) {
+#pragma unroll
+          for (int sh = 0; sh < 9; sh++, it++) {
+            const int dy = sh / 3 - 1, dx = sh % 3 - 1;
+            const int s = it % C_::STAGES;
+            const uint32_t par = (it / C_::STAGES) & 1;
+            mbar_wait(&full_bar[s], par);
+            tcgen05_fence_after();
+            const uint64_t stage_off = (uint64_t)((uint32_t)s * (uint32_t)(C_::STAGE_BYTES >> 4));
+            int j = 0;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+              if (!phase_uses(p >> 1, dy) || !phase_uses(p & 1, dx)) continue;
+              const uint32_t tmem_c = tmem_base + acc * BN + p * 64;
+#pragma unroll
+              for (int k = 0; k < 64 / UMMA_K; k++) {
+                const uint64_t da = da0 + stage_off + (uint64_t)(k * (32 >> 4));
+                const uint64_t db = db0 + stage_off + (uint64_t)(j * (B_TILE_BYTES >> 4)) + (uint64_t)(k * ((UMMA_K * 128) >> 4));
+                umma_bf16(tmem_c, da, db, idesc, (((started >> p) & 1u) || k > 0) ? 1u : 0u);
+              }
+              started |= 1u << p;
+              j++;
+            }
+            umma_commit(&empty_bar[s]);
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue: one 64-column round per output-parity phase =====================
+    const int q = warp & 3;
+    __shared__ float bias_s[64];
+    __shared__ float2 stat_s[STAT ? 2 * 4 * BN : 1];
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
+      const int mt = (tiles_n == 1) ? t : t / tiles_n, nt = (tiles_n == 1) ? 0 : t - mt * tiles_n;
+      const int n0 = nt * 64;
+      const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
+      const int rt = q * 32 + lane;
+      int pn0, py0;
+      pix_block(mt, 128, g.H, g.W, g.bh128, g.bn128, pn0, py0);
+      const int HW = g.H * g.W;
+      int nn, yy, xx;
+      if (HW >= 128) { nn = 0; yy = rt / g.W; xx = rt - yy * g.W; }
+      else { nn = rt / HW; const int rem = rt - nn * HW; yy = rem / g.W; xx = rem - yy * g.W; }
+      const int n = pn0 + nn, y = py0 + yy;
+      const bool row_ok = (n < g.N) && (y < g.H);
+      int n2 = n;
+      if (addend != nullptr && row_ok) n2 = grp_src[n / g.imgs_per_group] * g.imgs_per_group + (n % g.imgs_per_group);
+      const bool use_add = addend != nullptr && row_ok;
+      epi_bar_sync();   // every warp is done with bias_s of the previous tile
+      if (rt < 64) bias_s[rt] = (bias != nullptr) ? bias[n0 + rt] : 0.f;
+      epi_bar_sync();
+      float4 a4[16];
+      if (use_add) {   // skip addend of phase 0, requested before the accumulator is waited for
+        const float* ar = addend + (((long long)n2 * (2 * g.H) + 2 * y) * (2 * g.W) + 2 * xx) * g.Cn + n0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(ar + 4 * j);
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int p = 0; p < 4; p++) {
+        const int oy = 2 * y + (p >> 1), ox = 2 * xx + (p & 1);
+        const long long out_row = ((long long)n * (2 * g.H) + oy) * (2 * g.W) + ox;
+        uint32_t v2[64];
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 64);
+        tmem_ld32(taddr, v2);
+        tmem_ld32(taddr + 32, v2 + 32);
+        if (p > 0 && use_add) {
+          const float* ar = addend + (((long long)n2 * (2 * g.H) + oy) * (2 * g.W) + ox) * g.Cn + n0;
+#pragma unroll
+          for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(ar + 4 * j);
+        }
+        tmem_ld_wait_dep(v2);
+        tmem_ld_wait_dep(v2 + 32);
+        if (p == 3) {   // the accumulator goes back to the MMA warp before the last stores
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t* v = v2 + 32 * h;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 32 * h + j);
+            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (use_add) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float4 x4 = a4[8 * h + j];
+              f[4 * j] += x4.x; f[4 * j + 1] += x4.y; f[4 * j + 2] += x4.z; f[4 * j + 3] += x4.w;
+            }
+          }
+          if (STAT) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float r = row_ok ? (c_bf16 ? bf16_round(f[j]) : f[j]) : 0.f;
+              s1[j] = r;
+              s2[j] = r * r;
+            }
+            const float cs = warp_colsum32(s1, lane), cq = warp_colsum32(s2, lane);
+            stat_s[(acc * 4 + q) * BN + p * 64 + h * 32 + lane] = make_float2(cs, cq);
+          }
+          if (!row_ok) continue;
+          if (c_bf16) {
+            bf16* crow = reinterpret_cast<bf16*>(Cv) + out_row * ldc + n0 + 32 * h;
+#pragma unroll
+            for (int j = 0; j < 32; j += 16)
+              st_global_256(crow + j, pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]), pack_bf16x2(f[j + 4], f[j + 5]),
+                            pack_bf16x2(f[j + 6], f[j + 7]), pack_bf16x2(f[j + 8], f[j + 9]), pack_bf16x2(f[j + 10], f[j + 11]),
+                            pack_bf16x2(f[j + 12], f[j + 13]), pack_bf16x2(f[j + 14], f[j + 15]));
+          } else {
+            float* crow = reinterpret_cast<float*>(Cv) + out_row * ldc + n0 + 32 * h;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              st_global_256(crow + j, __float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]), __float_as_uint(f[j + 3]),
+                            __float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]), __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7]));
+          }
+        }
+      }
+      if (STAT) {
+        epi_bar_sync();
+        for (int i = q * 32 + lane; i < BN; i += 128) {
+          const int p = i >> 6, ch = i & 63;
+          const float2 a = stat_s[(acc * 4 + 0) * BN + i], b = stat_s[(acc * 4 + 1) * BN + i];
+          const float2 c2 = stat_s[(acc * 4 + 2) * BN + i], d = stat_s[(acc * 4 + 3) * BN + i];
+          stat_partial[((long long)mt * 4 + p) * g.Cn + n0 + ch] = make_float2((a.x + b.x) + (c2.x + d.x), (a.y + b.y) + (c2.y + d.y));
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ C, long long ldc, int M, int N,
                                           int accumulate) {
   const long long total = (long long)M * N;
@@ -435,6 +686,8 @@ int g_sms = 148;
 int g_k1_wide_max = 1 << 30;  // kind 1: 256-wide tiles while there are at most this many 128-wide output tiles (P2PVG_K1_WIDE_MAX)
 int g_bn256 = 1;  // P2PVG_CONV_BN256=0 keeps the 128-wide tiles (A/B comparison)
 int g_attr[2][3][3] = {};
+int g_convt4_max_cn = 128;  // kind 2 with at most this many output channels: the four parity phases fused into one tile (P2PVG_CONVT4_MAX_CN; 0 = off)
+int g_convt4_attr[2] = {};
 
 void resolve2() {
   int dev = 0, sms = 0;
@@ -446,6 +699,8 @@ void resolve2() {
   (void)cudaGetLastError();
   const char* e = getenv("P2PVG_CONV_BN256");
   if (e != nullptr && e[0] == '0') g_bn256 = 0;
+  const char* f4 = getenv("P2PVG_CONVT4_MAX_CN");
+  if (f4 != nullptr) g_convt4_max_cn = atoi(f4);
   const char* w = getenv("P2PVG_K1_WIDE_MAX");
   if (w != nullptr) g_k1_wide_max = atoi(w);
 }
@@ -527,6 +782,28 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype,
   return p2pvg_check_launch("conv_gemm");
 }
 
+int launch_convt4(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_dtype, long long ldc, const Geom& g, const float* bias,
+                  const float* addend, const int* grp_src, float2* stat_partial, cudaStream_t st) {
+  const bool stat = stat_partial != nullptr;
+  int& done = g_convt4_attr[stat];
+  if (!done) {
+    cudaError_t e = stat ? cudaFuncSetAttribute(convt4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES)
+                         : cudaFuncSetAttribute(convt4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      p2pvg_set_error("conv_gemm (fused phases): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return P2PVG_ERR_CUDA;
+    }
+    done = 1;
+  }
+  const long long tiles = (long long)cdiv(g.M, BLOCK_M) * (g.Cn / 64);
+  const int grid = (int)(tiles < g_sms ? tiles : g_sms);
+  if (stat)
+    convt4_kernel<true><<<grid, NUM_THREADS, Cfg<256>::SMEM_BYTES, st>>>(ta, tb, C, c_dtype == P2PVG_BF16, ldc, g, bias, addend, grp_src, stat_partial);
+  else
+    convt4_kernel<false><<<grid, NUM_THREADS, Cfg<256>::SMEM_BYTES, st>>>(ta, tb, C, c_dtype == P2PVG_BF16, ldc, g, bias, addend, grp_src, nullptr);
+  return p2pvg_check_launch("conv_gemm (fused phases)");
+}
+
 }  // namespace
 
 // a, b: see the kind table at the top.  H, W: SMALL-map size.  Returns P2PVG_ERR_UNSUPPORTED when the shape does not
@@ -585,6 +862,9 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
     rc = map2d(&tb, b, 16LL * Cn, Ck, ldb, 64);  // MN-major weight [Ck rows][16*Cn]
     if (rc) return rc;
     const int nkb = 4 * (Ck / 64);
+    if (Cn % 64 == 0 && Cn <= g_convt4_max_cn && !accumulate && (ldc % 16 == 0) && (c_dtype == P2PVG_F32 || ldc % 32 == 0) &&
+        ((uintptr_t)c & 31) == 0 && (addend == nullptr || ((uintptr_t)addend & 15) == 0))
+      return launch_convt4(ta, tb, c, c_dtype, ldc, g, bias, addend, grp_src, stat_partial, st);
     const int BN = (Cn % 256 == 0 && g_bn256) ? 256 : Cn > 64 ? 128 : 64;
     if (BN == 256) return launch<2, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
     if (BN == 128) return launch<2, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);

@@ -20,6 +20,10 @@ echo "== same for vgg_64 (C3): off, 0, 131072, 262144" >> $O/ab.txt
 for v in off 0 131072 262144; do
   if [ $v = off ]; then P2PVG_BN_FUSE=0 ts --steps 5 --backbone vgg_64 --channels 3 --batch 128 >> $O/ab.txt; else P2PVG_BN_FUSE_MIN=$v ts --steps 5 --backbone vgg_64 --channels 3 --batch 128 >> $O/ab.txt; fi
 done
+echo "== fused ConvT phases: max Cn 0 (off), 64, 128 (default), 256 (C2)" >> $O/ab.txt
+for v in 0 64 128 256; do P2PVG_CONVT4_MAX_CN=$v ts --steps 10 >> $O/ab.txt; done
+echo "== fused ConvT phases off / on (C4 dcgan_128 B=64)" >> $O/ab.txt
+for v in 0 128; do P2PVG_CONVT4_MAX_CN=$v ts --steps 10 --backbone dcgan_128 --channels 3 --batch 64 >> $O/ab.txt; done
 echo "== overlap heavy forks (P2PVG_OVERLAP=1) (C2)" >> $O/ab.txt
 P2PVG_OVERLAP=1 ts --steps 10 >> $O/ab.txt
 timeout 300 python bench.py --config C2 --steps 10 --warmup 3 --skip-cpu --skip-library > $O/bench_C2.json 2> $O/bench_C2.err; echo "bench C2 rc=$?" >> $O/rc.txt
