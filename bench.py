@@ -429,11 +429,13 @@ def main():
         K.gemm = timed_gemm
         K.conv_gemm = timed_conv
         saved_dist, eng.dist = eng.dist, None  # rank-0-only pass: no collectives
+        eng._serial = True                     # one stream: a GEMM must not share the GPU with a side lane while it is timed
         try:
             np.random.seed(0)
             eng.step(x_dev, use_graph=False, return_device=True)
             torch.cuda.synchronize()
         finally:
+            eng._serial = False
             eng.dist = saved_dist
             del K.gemm, K.conv_gemm   # instance attributes shadowing the methods
         tms = sum(r[0].elapsed_time(r[1]) for r in rec)

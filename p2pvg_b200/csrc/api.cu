@@ -80,6 +80,8 @@ bool p2pvg_lstm_cluster_supported(int);
 int p2pvg_lstm_cluster_fwd_impl(const float*, const float*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
 int p2pvg_lstm_cluster_bwd_impl(const float*, const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int p2pvg_lstm_scan_bwd_impl(const float*, const float*, const float*, const float*, float*, int, int, int, int, unsigned*, cudaStream_t);
+int p2pvg_lstm_cluster512_fwd_impl(const float*, const float*, const float*, float*, float*, float*, int, int, cudaStream_t);
+int p2pvg_lstm_cluster512_bwd_impl(const float*, const float*, const float*, const float*, float*, int, int, cudaStream_t);
 int p2pvg_reparam_kl_fwd_impl(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, int,
                               float*, cudaStream_t);
 int p2pvg_reparam_kl_bwd_impl(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
@@ -251,19 +253,23 @@ int p2pvg_lstm_pointwise_bwd(const float* dh, const float* dc_next, const float*
                              float* dgates, float* dc_prev, int B, int R, void* stream) {
   return p2pvg_lstm_pointwise_bwd_impl(dh, dc_next, gates, c_prev, c, dgates, dc_prev, B, R, ST);
 }
-// tensor-core mode: thread-block-cluster scans (lstm_cluster.cu) for R in {64,128,256}; P2PVG_LSTM_CLUSTER=0 keeps the
+// tensor-core mode: thread-block-cluster scans (lstm_cluster.cu) for R in {64,128,256}, lstm_cluster512.cu for R = 512; P2PVG_LSTM_CLUSTER=0 keeps the
 // cooperative-grid scans, which also serve the exact-fp32 mode
-static bool use_cluster_scan(int R) {
+static bool cluster_scan_enabled() {
   static const int off = [] { const char* e = getenv("P2PVG_LSTM_CLUSTER"); return (e != nullptr && e[0] == '0') ? 1 : 0; }();
-  return !off && p2pvg_lstm_cluster_supported(R);
+  return !off;
 }
+// R = 512 (BASELINE config 5) runs on clusters of 16 CTAs (lstm_cluster512.cu)
+static bool use_cluster_scan(int R) { return cluster_scan_enabled() && p2pvg_lstm_cluster_supported(R); }
 int p2pvg_lstm_scan_fwd(const float* pre, const float* whh, const float* bhh, float* gates, float* hs, float* cs, int S, int B, int R,
                         int tf32, unsigned* counter, void* stream) {
+  if (tf32 && R == 512 && cluster_scan_enabled()) return p2pvg_lstm_cluster512_fwd_impl(pre, whh, bhh, gates, hs, cs, S, B, ST);
   if (tf32 && use_cluster_scan(R)) return p2pvg_lstm_cluster_fwd_impl(pre, whh, bhh, gates, hs, cs, S, B, R, ST);
   return p2pvg_lstm_scan_fwd_impl(pre, whh, bhh, gates, hs, cs, S, B, R, tf32, counter, ST);
 }
 int p2pvg_lstm_scan_bwd(const float* dhtop, const float* whh, const float* gates, const float* cs, float* dG, int S, int B, int R,
                         int tf32, unsigned* counter, void* stream) {
+  if (tf32 && R == 512 && cluster_scan_enabled()) return p2pvg_lstm_cluster512_bwd_impl(dhtop, whh, gates, cs, dG, S, B, ST);
   if (tf32 && use_cluster_scan(R)) return p2pvg_lstm_cluster_bwd_impl(dhtop, whh, gates, cs, dG, S, B, R, ST);
   return p2pvg_lstm_scan_bwd_impl(dhtop, whh, gates, cs, dG, S, B, R, tf32, counter, ST);
 }

@@ -686,7 +686,9 @@ int g_sms = 148;
 int g_k1_wide_max = 1 << 30;  // kind 1: 256-wide tiles while there are at most this many 128-wide output tiles (P2PVG_K1_WIDE_MAX)
 int g_bn256 = 1;  // P2PVG_CONV_BN256=0 keeps the 128-wide tiles (A/B comparison)
 int g_attr[2][3][3] = {};
-int g_convt4_max_cn = 128;  // kind 2 with at most this many output channels: the four parity phases fused into one tile (P2PVG_CONVT4_MAX_CN; 0 = off)
+int g_convt4_max_cn = 64;   // kind 2 with at most this many output channels: the four parity phases fused into one tile (P2PVG_CONVT4_MAX_CN;
+                            // 0 = off).  Measured (C2 step, B200): 64 -> -0.36 ms; 128 -> +0.1 ms (the N = 64 MMAs of the fused tile issue twice as
+                            // many instructions as the 128-wide phase tiles, which outweighs the saved operand fills)
 int g_convt4_attr[2] = {};
 
 void resolve2() {

@@ -176,7 +176,9 @@ class TrainEngine:
         # one persistent cooperative launch per LSTM layer and direction instead of two launches per timestep
         # direct CUDA-core kernels for the 1/3-channel ends: measured slower than im2col + tcgen05 GEMM, so opt-in only
         self.thin = hasattr(kernels, "conv_thin_in") and os.environ.get("P2PVG_THIN", "0") == "1"
-        self.fused_scan = hasattr(kernels, "lstm_scan_fwd") and self.R % 64 == 0 and self.R <= 256 and os.environ.get("P2PVG_FUSED_SCAN", "1") != "0"
+        # (R = 512: clusters of 16 CTAs, tensor-core mode only -- the exact-fp32 cooperative grid cannot keep a 4 MB W_hh resident)
+        r512 = self.R == 512 and tc_lstm and os.environ.get("P2PVG_LSTM_CLUSTER", "1") != "0"
+        self.fused_scan = hasattr(kernels, "lstm_scan_fwd") and self.R % 64 == 0 and (self.R <= 256 or r512) and os.environ.get("P2PVG_FUSED_SCAN", "1") != "0"
         self.implicit = (act_dtype == torch.bfloat16) and hasattr(kernels, "conv_gemm") and os.environ.get("P2PVG_IMPLICIT", "1") != "0"
         # 1/3-channel ends (K = 16 nc or N = 16 nc < 64): four pixel rows are multiplied as one row against a block-diagonal
         # copy of the weight, so that no TMA box is out of bounds (measured 3x faster than the partially-OOB boxes)

@@ -12,8 +12,10 @@ def K():
 
 
 @pytest.mark.parametrize("tf32", [False, True])
-@pytest.mark.parametrize("S,B,R", [(5, 3, 64), (7, 70, 256), (30, 256, 256), (4, 100, 128)])
+@pytest.mark.parametrize("S,B,R", [(5, 3, 64), (7, 70, 256), (30, 256, 256), (4, 100, 128), (6, 40, 512), (9, 256, 512), (1, 17, 512)])
 def test_scan_fwd_bwd(K, S, B, R, tf32):
+    if R == 512 and not tf32 and B > 128:
+        pytest.skip("exact-fp32 R=512 uses the per-step kernels at this batch (the cooperative grid does not fit)")
     tol = 3e-3 if tf32 else 1e-4
     torch.manual_seed(0)
     dev = "cuda"

