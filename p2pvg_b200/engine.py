@@ -166,6 +166,7 @@ class TrainEngine:
             self.buffers[m] = {k: v.detach().clone().to(self.dev) for k, v in state[m].items() if not is_param_key(k)}
         self._bufs = {}
         self._buf_gen = 0
+        self._plans, self._uploaded = {}, None
         self._packed = {}
         self._graphs = {}
         self.dist = None  # (torch.distributed, group, world_size) when batch-sharded over several GPUs
@@ -390,12 +391,23 @@ class TrainEngine:
         opt = self.opt
         if probs is None:
             probs = np.random.uniform(0, 1, T - 1)
-        plan = StepPlan(T, probs, opt)
+        # the index tables only depend on WHICH timesteps execute: plans are cached per pattern, and a pattern that is already
+        # on the device (always the case with skip_prob = 0) is not uploaded again
+        sched = skip_schedule(T, probs, opt["skip_prob"], opt["n_past"])
+        pkey = (T, tuple(i for i, _, _ in sched), bool(opt["last_frame_skip"]), int(opt["n_past"]))
+        plan = self._plans.get(pkey)
+        if plan is None:
+            if len(self._plans) > 4096:
+                self._plans.clear()
+            plan = self._plans[pkey] = StepPlan(T, probs, opt)
         self.last_plan = plan
         self.T, self.B, self.S = T, B, plan.S
         if eps is None:
             eps = torch.randn(plan.S, 2, B, self.z, device=self.dev, dtype=torch.float32)
-        self.upload_plan(plan)
+        ukey = (pkey, B, float(opt["weight_cpc"]), self.graph_generation())
+        if ukey != self._uploaded:
+            self.upload_plan(plan)
+            self._uploaded = ukey
         if use_graph:
             out = self._step_graphed(x, eps, plan)
         else:
