@@ -61,7 +61,9 @@ int p2pvg_set_gemm_impl(int impl);
  * Replaces the library GEMMs behind nn.Conv2d / nn.ConvTranspose2d (models/dcgan_64.py:8,20,43,64,76 after
  * lowering), nn.Linear and nn.LSTMCell (models/lstm.py:13-17,54-57) and their autograd backward.
  * bf16 operands run on tcgen05 tensor cores (fp32 accumulation in TMEM); fp32 operands on CUDA cores (exact) unless
- * `flags` allows TF32 (see above).
+ * `flags` allows TF32 (see above).  Documented dispatch between two kernels of this library: bf16 operands whose base
+ * address or row pitch is not 16-byte aligned (not expressible as a TMA tensor map) run on the CUDA-core kernel with the
+ * same arithmetic contract; p2pvg_set_gemm_impl(2) turns that case into P2PVG_ERR_UNSUPPORTED.
  * workspace: split-K partials for the tensor-core path (may be NULL when ws_bytes == 0). */
 int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int c_dtype,
                int64_t ldc, int M, int N, int K, int accumulate, const float* bias, const void* addend, int64_t ldd,
@@ -226,6 +228,13 @@ int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act
 int p2pvg_mse_chunks(void);
 int p2pvg_sigmoid_mse(const void* raw, int dtype, const float* x, const int* tgt, const float* coef, int G, int64_t E,
                       void* pred, void* d_raw, float* partial, void* stream);
+/* The last decoder layer of the 1-channel dcgan stacks fused with its loss: ConvTranspose2d(2*64, 1, 4, 2, 1) + nn.Sigmoid
+ * (models/dcgan_64.py:75-79) + nn.MSELoss against frame tgt[g] (models/p2p_model.py:254,256).  col [G*B*Hi*Wi, 16] / col2
+ * [nsrc*B*Hi*Wi, 16]: the 16 tap products of every input pixel of the decoder half / of the shared skip half (group g uses
+ * skip source grp_src[g]), as produced by p2pvg_gemm.  Writes d(loss)/d(raw) [G, B*2Hi*2Wi] and the squared-error partials
+ * [G, p2pvg_mse_chunks()]; the raw output is never materialised. */
+int p2pvg_convt_c1_loss(const void* col, const void* col2, int dtype, const int* grp_src, const float* bias, const float* x, const int* tgt,
+                        const float* coef, int G, int B, int Hi, int Wi, void* d_raw, float* partial, void* stream);
 /* h36m pose backbone (models/h36m_mlp.py): nn.LayerNorm of residual_linear (:43,46) forward / backward (fp32, row-wise; dx may alias
  * dy; dgamma == NULL skips the parameter gradients) and the plain nn.MSELoss on [B,17,3] poses (models/p2p_model.py:254,256) with
  * the same partial-sum layout as p2pvg_sigmoid_mse. */

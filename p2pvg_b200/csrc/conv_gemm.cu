@@ -426,6 +426,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // statistics), one 64-column round per phase.
 __device__ __forceinline__ bool phase_uses(int a, int d) { return d == 0 || (d < 0 ? a == 0 : a == 1); }
 __device__ __forceinline__ int phase_tap(int a, int d) { return d == 0 ? a + 1 : (a ? 0 : 3); }
+// The accumulator holds the phases in the column-block order [p0, p1, p3, p2]: then the phases served by one shift are
+// NEIGHBOURS for the centre shift (all four) and three of the four edge shifts, so one 256- / 128-wide tcgen05.mma covers them
+// instead of four / two 64-wide ones (10 instead of 16 MMAs per 16-wide K slice and channel chunk: the single issuing thread
+// was the limit of the 64-wide version).  The centre shift comes FIRST in every tile so that all four column blocks start
+// accumulating together.
+__device__ __forceinline__ int cb_phase(int cb) { return cb == 2 ? 3 : cb == 3 ? 2 : cb; }   // involution: block <-> phase
+__device__ __forceinline__ void shift_of(int so, int& dy, int& dx) {
+  // 0 centre; 1..4 edges (-1,0) (+1,0) (0,+1) (0,-1); 5..8 corners
+  dy = (so == 1 || so == 5 || so == 6) ? -1 : (so == 2 || so == 7 || so == 8) ? 1 : 0;
+  dx = (so == 4 || so == 5 || so == 7) ? -1 : (so == 3 || so == 6 || so == 8) ? 1 : 0;
+}
+__device__ __forceinline__ bool cb_used(int cb, int dy, int dx) {
+  const int p = cb_phase(cb);
+  return phase_uses(p >> 1, dy) && phase_uses(p & 1, dx);
+}
 
 template <bool STAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -482,8 +497,9 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int cc = 0; cc < cchunks; cc++) {
           const int c0 = cc * 64;
 #pragma unroll
-          for (int sh = 0; sh < 9; sh++, it++) {
-            const int dy = sh / 3 - 1, dx = sh % 3 - 1;
+          for (int so = 0; so < 9; so++, it++) {
+            int dy, dx;
+            shift_of(so, dy, dx);
             const int nb = (dy == 0 ? 2 : 1) * (dx == 0 ? 2 : 1);
             const int s = it % C_::STAGES;
             const uint32_t par = (it / C_::STAGES) & 1;
@@ -494,10 +510,10 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tma_load_4d(&tmA, &full_bar[s], sa, c0, dx, py0 + dy, pn0);
             int j = 0;
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-              const int a = p >> 1, b = p & 1;
-              if (!phase_uses(a, dy) || !phase_uses(b, dx)) continue;
-              const int ky = phase_tap(a, dy), kx = phase_tap(b, dx);
+            for (int cb = 0; cb < 4; cb++) {   // weight taps in accumulator column-block order
+              if (!cb_used(cb, dy, dx)) continue;
+              const int p = cb_phase(cb);
+              const int ky = phase_tap(p >> 1, dy), kx = phase_tap(p & 1, dx);
               tma_load_2d(&tmB, &full_bar[s], sb + j * B_TILE_BYTES, (ky * 4 + kx) * g.Cn + nt * 64, c0);
               j++;
             }
@@ -508,8 +524,7 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
-                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BLOCK_M >> 4) << 24);
       const uint32_t smem0 = smem_u32(smem);
       const uint64_t da0 = make_desc(smem0, 0, 1024);
       const uint64_t db0 = make_desc(smem0 + A_STAGE_BYTES, 64 * 128, 1024);
@@ -518,11 +533,11 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tcgen05_fence_after();
-        uint32_t started = 0;   // bit p: phase p's columns hold a partial sum of this tile
         for (int cc = 0; cc < cchunks; cc++) {
 #pragma unroll
-          for (int sh = 0; sh < 9; sh++, it++) {
-            const int dy = sh / 3 - 1, dx = sh % 3 - 1;
+          for (int so = 0; so < 9; so++, it++) {
+            int dy, dx;
+            shift_of(so, dy, dx);
             const int s = it % C_::STAGES;
             const uint32_t par = (it / C_::STAGES) & 1;
             mbar_wait(&full_bar[s], par);
@@ -530,17 +545,21 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint64_t stage_off = (uint64_t)((uint32_t)s * (uint32_t)(C_::STAGE_BYTES >> 4));
             int j = 0;
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-              if (!phase_uses(p >> 1, dy) || !phase_uses(p & 1, dx)) continue;
-              const uint32_t tmem_c = tmem_base + acc * BN + p * 64;
+            for (int cb = 0; cb < 4;) {
+              if (!cb_used(cb, dy, dx)) { cb++; continue; }
+              int len = 1;
+              while (cb + len < 4 && cb_used(cb + len, dy, dx)) len++;   // neighbouring column blocks: one wide MMA
+              const uint32_t idesc = idesc0 | ((uint32_t)((64 * len) >> 3) << 17);
+              const uint32_t tmem_c = tmem_base + acc * BN + cb * 64;
 #pragma unroll
               for (int k = 0; k < 64 / UMMA_K; k++) {
                 const uint64_t da = da0 + stage_off + (uint64_t)(k * (32 >> 4));
                 const uint64_t db = db0 + stage_off + (uint64_t)(j * (B_TILE_BYTES >> 4)) + (uint64_t)(k * ((UMMA_K * 128) >> 4));
-                umma_bf16(tmem_c, da, db, idesc, (((started >> p) & 1u) || k > 0) ? 1u : 0u);
+                // the centre shift of channel chunk 0 is the first product of every column block of the tile
+                umma_bf16(tmem_c, da, db, idesc, (cc > 0 || so > 0 || k > 0) ? 1u : 0u);
               }
-              started |= 1u << p;
-              j++;
+              j += len;
+              cb += len;
             }
             umma_commit(&empty_bar[s]);
           }
@@ -582,21 +601,22 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int p = 0; p < 4; p++) {
+      for (int cbi = 0; cbi < 4; cbi++) {
+        const int p = cb_phase(cbi);   // accumulator column block cbi holds output parity p
         const int oy = 2 * y + (p >> 1), ox = 2 * xx + (p & 1);
         const long long out_row = ((long long)n * (2 * g.H) + oy) * (2 * g.W) + ox;
         uint32_t v2[64];
-        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 64);
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(cbi * 64);
         tmem_ld32(taddr, v2);
         tmem_ld32(taddr + 32, v2 + 32);
-        if (p > 0 && use_add) {
+        if (cbi > 0 && use_add) {
           const float* ar = addend + (((long long)n2 * (2 * g.H) + oy) * (2 * g.W) + ox) * g.Cn + n0;
 #pragma unroll
           for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(ar + 4 * j);
         }
         tmem_ld_wait_dep(v2);
         tmem_ld_wait_dep(v2 + 32);
-        if (p == 3) {   // the accumulator goes back to the MMA warp before the last stores
+        if (cbi == 3) {   // the accumulator goes back to the MMA warp before the last stores
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);

@@ -35,6 +35,57 @@ __global__ void __launch_bounds__(256) sigmoid_mse_kernel(const T* __restrict__ 
   }
 }
 
+// K5 of SURVEY.md §2.2: the last decoder layer -- ConvTranspose2d(2*64 -> 1, 4, 2, 1) + Sigmoid (models/dcgan_64.py:75-79) --
+// fused with the reconstruction / CPC loss (nn.MSELoss, models/p2p_model.py:254,256).  The 16-tap products of every input
+// pixel come from the tcgen05 GEMMs (col [N*Hi*Wi, 16] for the decoder path, col2 for the shared skip path); this kernel
+// gathers the four taps of an output pixel from both, adds the bias, applies the sigmoid, accumulates the squared error
+// against the target frame and writes d(loss)/d(raw) -- one pass, no raw-output tensor, 32-bit index arithmetic.
+template <typename T>
+__global__ void __launch_bounds__(256) convt_c1_loss_kernel(const T* __restrict__ col, const T* __restrict__ col2, const int* __restrict__ grp_src,
+                                                            const float* __restrict__ bias, const float* __restrict__ x,
+                                                            const int* __restrict__ tgt, const float* __restrict__ coef, int B, int Hi,
+                                                            int Wi, T* __restrict__ d_raw, float* __restrict__ partial) {
+  const int g = blockIdx.y;
+  const unsigned Ho = 2u * Hi, Wo = 2u * Wi;
+  const unsigned E = (unsigned)B * Ho * Wo;
+  const float* xt = x + (long long)tgt[g] * E;
+  const T* cg = col + (long long)g * B * Hi * Wi * 16;
+  const T* sg = col2 + (long long)grp_src[g] * B * Hi * Wi * 16;
+  T* dg = d_raw + (long long)g * E;
+  const float cf = coef[g], b0 = bias ? bias[0] : 0.f;
+  double acc = 0.0;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const unsigned ox = e % Wo, r = e / Wo, oy = r % Ho, b = r / Ho;
+    const int kh0 = (oy + 1) & 1, kw0 = (ox + 1) & 1;
+    float v = b0;
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int kh = kh0 + 2 * a, kw = kw0 + 2 * c;
+        const int ty = (int)oy + 1 - kh, tx = (int)ox + 1 - kw;
+        const int iy = ty >> 1, ix = tx >> 1;
+        if (ty < 0 || iy >= Hi || tx < 0 || ix >= Wi) continue;
+        const unsigned off = (((b * Hi + iy) * Wi + ix) << 4) + kh * 4 + kw;
+        v += ld_f<T>(cg + off) + ld_f<T>(sg + off);
+      }
+    }
+    const float s = sigmoidf_(v);
+    const float d = s - xt[e];
+    acc += (double)d * (double)d;
+    st_f<T>(dg + e, cf * 2.f * d * s * (1.f - s));
+  }
+  __shared__ double sh[8];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < 8; w++) v += sh[w];
+    partial[(long long)g * gridDim.x + blockIdx.x] = (float)v;
+  }
+}
+
 __global__ void finalize_losses_kernel(const float* __restrict__ mse_partial, int n_recon, int has_cpc, int nchunk, double E,
                                        const float* __restrict__ kl_sum, float batch_size, const float* __restrict__ align_partial,
                                        int n_align, float seq_len, float* __restrict__ out) {
@@ -97,6 +148,16 @@ int p2pvg_sigmoid_mse_impl(const void* raw, int dtype, const float* x, const int
   dim3 grid(MSE_CHUNKS, G);
   DISPATCH_DTYPE(dtype, T, (sigmoid_mse_kernel<T><<<grid, 256, 0, st>>>((const T*)raw, x, tgt, coef, E, (T*)pred, (T*)d_raw, partial)));
   return p2pvg_check_launch("sigmoid_mse");
+}
+
+int p2pvg_convt_c1_loss_impl(const void* col, const void* col2, int dtype, const int* grp_src, const float* bias, const float* x, const int* tgt,
+                             const float* coef, int G, int B, int Hi, int Wi, void* d_raw, float* partial, cudaStream_t st) {
+  if (G == 0 || B == 0) return P2PVG_OK;
+  P2PVG_REQUIRE((long long)B * Hi * Wi * 16 < (1LL << 31), P2PVG_ERR_UNSUPPORTED, "convt_c1_loss: group too large for 32-bit indexing");
+  dim3 grid(MSE_CHUNKS, G);
+  DISPATCH_DTYPE(dtype, T, (convt_c1_loss_kernel<T><<<grid, 256, 0, st>>>((const T*)col, (const T*)col2, grp_src, bias, x, tgt, coef, B, Hi, Wi,
+                                                                          (T*)d_raw, partial)));
+  return p2pvg_check_launch("convt_c1_loss");
 }
 
 int p2pvg_finalize_losses_impl(const float* mse_partial, int n_recon, int has_cpc, double E, const float* kl_sum, float batch_size,

@@ -190,6 +190,8 @@ class TrainEngine:
         # persistent GEMMs leave little room for a co-resident kernel -- so it is opt-in: P2PVG_OVERLAP=1.
         # BatchNorm forward statistics come out of the producing implicit GEMM's epilogue (per-tile column sums) instead of a
         # separate pass over the stored tensor; P2PVG_BN_FUSE=0 keeps the stand-alone statistics kernel (A/B comparison)
+        # 1-channel stacks: tap gather + sigmoid + MSE of the last decoder layer as one kernel (no raw-output tensor)
+        self.fuse_last = hasattr(kernels, "convt_c1_loss") and act_dtype == torch.bfloat16 and os.environ.get("P2PVG_FUSE_LAST", "1") != "0"
         self.fuse_stats = self.implicit and os.environ.get("P2PVG_BN_FUSE", "1") != "0"
         # ... but only where the tile's MMA time hides the extra epilogue work: reduction length x tile width of the GEMM must
         # reach this many MACs per output row (measured: low-K tiles are epilogue-bound and get slower)
@@ -775,7 +777,7 @@ class TrainEngine:
             Mo = N * 4 * Hi * Hi
             raw = self.buf(f"dec_raw{k}", Mo * cout)
             imp = self.implicit and cd % 64 == 0 and cout % 64 == 0
-            sp = None
+            sp = rec_fused = None
             if imp:
                 # skip half once per distinct source frame (fp32, bias folded in), added in the epilogue of the main GEMM
                 addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
@@ -797,8 +799,12 @@ class TrainEngine:
                 else:
                     K.gemm(d, wD, colD, Md, 16 * cout, cd, b_mn=True)
                     K.gemm(skip, wS, colS, Ms, 16 * cout, cd, b_mn=True)
-                K.col2im(colD, raw, N, Hi, Hi, cout, bias=P[cn + ".bias"], col2=colS, grp_src=self.ix["skip_src"], imgs_per_group=B)
-            rec = dict(inp=d, skip=skip, raw=raw, cd=cd, cout=cout, Hi=Hi, Md=Md, Ms=Ms, imp=imp,
+                if k == n - 1 and cout == 1 and self.fuse_last:
+                    # last layer of a 1-channel stack: the tap gather, sigmoid and loss run as ONE kernel in losses_fwd
+                    rec_fused = (colD, colS, Hi, P[cn + ".bias"])
+                else:
+                    K.col2im(colD, raw, N, Hi, Hi, cout, bias=P[cn + ".bias"], col2=colS, grp_src=self.ix["skip_src"], imgs_per_group=B)
+            rec = dict(inp=d, skip=skip, raw=raw, cd=cd, cout=cout, Hi=Hi, Md=Md, Ms=Ms, imp=imp, fused_loss=rec_fused,
                        thin=(not imp) and self.thin and cout <= 3 and cd % 8 == 0)
             if k < n - 1:
                 dn = self.buf(f"dec_d{k}", Mo * cout)
@@ -821,7 +827,13 @@ class TrainEngine:
         raw = self.dec[-1]["raw"]
         self.d_rawout = self.buf("dec_d_rawout", G * E)
         self.mse_partial = self.fbuf("mse_partial", G * K.mse_chunks())
-        K.sigmoid_mse(raw, self.x_nhwc, self.ix["tgt_idx"], self.coef, G, E, None, self.d_rawout, self.mse_partial)
+        fl = self.dec[-1].get("fused_loss")
+        if fl is not None:
+            colD, colS, Hi, bias = fl
+            K.convt_c1_loss(colD, colS, self.ix["skip_src"], bias, self.x_nhwc, self.ix["tgt_idx"], self.coef, G, B, Hi, Hi,
+                            self.d_rawout, self.mse_partial)
+        else:
+            K.sigmoid_mse(raw, self.x_nhwc, self.ix["tgt_idx"], self.coef, G, E, None, self.d_rawout, self.mse_partial)
         self.align_partial = self.fbuf("align_partial", max(S, 1))
         self.d_hpred = self.fbuf("d_hpred", G * B * self.g)
         self.dH = self.fbuf("dH", self.T * B * self.g)
