@@ -245,7 +245,8 @@ class TrainEngine:
                 ev = torch.cuda.Event()
                 ev.record(self.streams[lane])
                 torch.cuda.current_stream(self.dev).wait_event(ev)
-                self._dirty.discard(lane)
+                if self.K.lane == 0:   # a side lane that joins another one does not relieve lane 0 of its own join
+                    self._dirty.discard(lane)
 
     def lbuf(self, name, numel, dtype=None):
         """Scratch buffer private to the lane that is enqueueing (concurrent lanes must not share scratch)."""

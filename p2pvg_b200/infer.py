@@ -281,6 +281,22 @@ def p2p_generate(model, x, len_output, eval_cp_ix, model_mode="full", skip_frame
     return gen_seq
 
 
+@torch.no_grad()
+def p2p_generate_samples(model, x, nsample, len_output, eval_cp_ix, model_mode="full", skip_frame=False):
+    """`nsample` independent samples for every input sequence in ONE autoregressive pass: the batch is
+    tiled nsample times, so every kernel of a step runs once on nsample*B rows instead of nsample times on B rows
+    (misc/visualize.py:135-144 loops `nsample` = 20 calls of p2p_generate).  In eval mode (BatchNorm on running statistics)
+    rows are independent, so sample s equals what a separate call with the same noise draws would return; the NumPy
+    frame-skip pattern (skip_frame=True) is drawn once and shared by the samples of a call.
+    Returns a list of nsample sequences (each a list of len_output frames [B, ...])."""
+    if isinstance(x, tuple):
+        x = x[1]
+    B = int(x[0].shape[0])
+    tiled = [f.repeat(nsample, *([1] * (f.dim() - 1))) for f in x]
+    seq = p2p_generate(model, tiled, len_output, eval_cp_ix, model_mode=model_mode, skip_frame=skip_frame)
+    return [[f[s * B:(s + 1) * B] for f in seq] for s in range(nsample)]
+
+
 # ---- human3.6m pose backbone (reference models/h36m_mlp.py:45-46, 61-69, 85-95) -----------------------------------------
 def _linear(K, lin, x, rows, act=None):
     out = torch.empty(rows, lin.out_features, device=x.device)

@@ -184,6 +184,11 @@ class P2PModel(nn.Module):
         from ..infer import p2p_generate
         return p2p_generate(self, x, len_output, eval_cp_ix, model_mode=model_mode, skip_frame=skip_frame, init_hidden=init_hidden)
 
+    def p2p_generate_samples(self, x, nsample, len_output, eval_cp_ix, model_mode='full', skip_frame=False):
+        """nsample samples per input sequence in one batched pass (an addition to the reference API; see infer.py)."""
+        from ..infer import p2p_generate_samples
+        return p2p_generate_samples(self, x, nsample, len_output, eval_cp_ix, model_mode=model_mode, skip_frame=skip_frame)
+
     # ---- checkpoints (same dict layout as reference p2p_model.py:289-330) --------------------------
     def save(self, fname, epoch):
         backbone_net, optimizer = self.opt.backbone_net, getattr(self.opt, "optimizer", None)

@@ -101,3 +101,34 @@ def test_resume_from_reference_checkpoint():
             del os.environ["P2PVG_PRECISION"]
         else:
             os.environ["P2PVG_PRECISION"] = prev
+
+
+def test_batched_samples_equal_looped_calls():
+    """p2p_generate_samples (nsample tiled along the batch, one pass) against nsample separate p2p_generate calls fed the
+    same noise draws (fp32 mode: rows are independent in eval mode)."""
+    from p2pvg_b200.infer import eps_stream
+    fix = torch.load(GEN[0], weights_only=False)
+    prev = os.environ.get("P2PVG_PRECISION")
+    os.environ["P2PVG_PRECISION"] = "fp32"
+    try:
+        model = build_model(fix)
+        x = fix["x"].cuda()
+        B, z, ns, L = x.shape[1], 10, 3, fix["len_output"]
+        n_exec = L - 1
+        g = torch.Generator().manual_seed(9)
+        draws = torch.randn(ns, n_exec, 2, B, z, generator=g)
+        looped = []
+        for s in range(ns):
+            with eps_stream([draws[s, i, j] for i in range(n_exec) for j in (0, 1)]):
+                looped.append(model.p2p_generate(x, L, L - 1, model_mode="full", skip_frame=False))
+        with eps_stream([draws[:, i, j].reshape(ns * B, z) for i in range(n_exec) for j in (0, 1)]):
+            batched = model.p2p_generate_samples(x, ns, L, L - 1, model_mode="full", skip_frame=False)
+        assert len(batched) == ns and len(batched[0]) == L
+        for s in range(ns):
+            for a, b in zip(batched[s], looped[s]):
+                assert a.shape == b.shape and torch.allclose(a.float(), b.float(), rtol=1e-4, atol=2e-5)
+    finally:
+        if prev is None:
+            del os.environ["P2PVG_PRECISION"]
+        else:
+            os.environ["P2PVG_PRECISION"] = prev
