@@ -411,6 +411,40 @@ int launch_cluster16(Kern kern, const char* what, int grid, size_t smem, cudaStr
 
 }  // namespace
 
+// cudaOccupancyMaxActiveClusters of the cluster-16 scans (which = 0: forward MT=1, 1: forward MT=2, 2: backward); diagnostics
+int p2pvg_lstm_cluster512_max_clusters_impl(int which) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS * 64);
+  cfg.blockDim = dim3(NT);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = -1;
+  cudaError_t e;
+  if (which == 0) {
+    cfg.dynamicSmemBytes = fwd_smem(1);
+    cudaFuncSetAttribute(lstm_cl16_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(1));
+    cudaFuncSetAttribute(lstm_cl16_fwd_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl16_fwd_kernel<1>, &cfg);
+  } else if (which == 1) {
+    cfg.dynamicSmemBytes = fwd_smem(2);
+    cudaFuncSetAttribute(lstm_cl16_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(2));
+    cudaFuncSetAttribute(lstm_cl16_fwd_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl16_fwd_kernel<2>, &cfg);
+  } else {
+    cfg.dynamicSmemBytes = bwd_smem();
+    cudaFuncSetAttribute(lstm_cl16_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem());
+    cudaFuncSetAttribute(lstm_cl16_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl16_bwd_kernel, &cfg);
+  }
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  return n;
+}
+
 // rows per slab of the forward scan: 32 above this batch size (8 clusters of 16 CTAs = one wave for 256 rows)
 int p2pvg_lstm_cluster512_fwd_impl(const float* pre, const float* whh, const float* bhh, float* gates, float* hs, float* cs, int S, int B,
                                    cudaStream_t st) {

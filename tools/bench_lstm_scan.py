@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from p2pvg_b200._lib import CudaKernels  # noqa: E402
 
 K = CudaKernels("cuda")
+print("cluster-16 scans: cudaOccupancyMaxActiveClusters fwd(16 rows) / fwd(32 rows) / bwd =",
+      [K.lib.p2pvg_lstm_cluster512_max_clusters(i) for i in range(3)])
 S, R = 30, int(os.environ.get("R", "256"))
 for B in (16, 64, 128, 256):
     dev = "cuda"
