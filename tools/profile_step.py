@@ -12,23 +12,29 @@ import types
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from p2pvg_b200.models import dcgan_64  # noqa: E402
+from p2pvg_b200.models import dcgan_64, dcgan_128, h36m_mlp, vgg_64  # noqa: E402
 from p2pvg_b200.models.p2p_model import P2PModel  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--seq", type=int, default=30)
+ap.add_argument("--backbone", default="dcgan_64", choices=["dcgan_64", "dcgan_128", "vgg_64", "h36m_mlp"])
+ap.add_argument("--channels", type=int, default=1)
+ap.add_argument("--rnn", type=int, default=256)
 ap.add_argument("--phases", action="store_true")
 ap.add_argument("--calls", action="store_true", help="time every kernel-API call with CUDA events (last step)")
 args = ap.parse_args()
 os.environ["P2PVG_GRAPH"] = "0"
-opt = types.SimpleNamespace(dataset="mnist", backbone_net=dcgan_64, lr=1e-3, beta1=0.9, beta=1e-4, weight_cpc=100.0, weight_align=0.5,
+net = dict(dcgan_64=dcgan_64, dcgan_128=dcgan_128, vgg_64=vgg_64, h36m_mlp=h36m_mlp)[args.backbone]
+pose = args.backbone == "h36m_mlp"
+width = 128 if args.backbone.endswith("128") else 64
+opt = types.SimpleNamespace(dataset="h36m" if pose else "mnist", backbone_net=net, lr=1e-3, beta1=0.9, beta=1e-4, weight_cpc=100.0, weight_align=0.5,
                             skip_prob=0.0, n_past=1, last_frame_skip=False, batch_size=args.batch)
 torch.manual_seed(1)
-model = P2PModel(args.batch, 1, 128, 10, 256, 1, 1, 2, opt=opt).cuda()
-x = torch.rand(args.seq, args.batch, 1, 64, 64, device="cuda")
-eng = model.engine(64)
+model = P2PModel(args.batch, args.channels, 128, 10, args.rnn, 1, 1, 2, opt=opt).cuda()
+x = 3 * torch.randn(args.seq, args.batch, 17, 3, device="cuda") if pose else torch.rand(args.seq, args.batch, args.channels, width, width, device="cuda")
+eng = model.engine(width)
 calls = []
 
 
