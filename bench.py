@@ -463,12 +463,14 @@ def main():
     # ---- per-phase device times and the LSTM HBM roofline ------------------------------------------
     if rank == 0 and not args.skip_phases:
         phases = eng.time_phases(x_dev)
+        tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
+        lstm_traffic = json.load(open(tp)).get("C5") if (pose and os.path.exists(tp)) else None
         t_lstm = phases["lstm_fwd"] + phases["lstm_bwd"] + phases["prior_bwd"]
         model_bytes, q_fwd = lstm_model_bytes(c, S_meas, B)
         ach = model_bytes / (t_lstm * 1e-3) / 1e9
         roof_lstm = dict(bound="hbm", kernel="recurrent phases: lstm_cl_{fwd,bwd} cluster scans + input / head GEMMs + reparam_kl + concat "
                                              "(posterior, prior, frame predictor; forward, BPTT #1, prior BPTT #2 incl. the CPC chain)",
-                         achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None, peak_source=pk["which"],
+                         achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=lstm_traffic, peak_source=pk["which"],
                          model_bytes_per_step=model_bytes, q_fwd_bytes=q_fwd, executed_timesteps=S_meas, phase_ms=t_lstm,
                          note="model bytes S*3*Q_fwd of SURVEY §8(d); the cluster scans keep W_hh in registers and move fewer HBM bytes "
                               "than the model, so this is a time-to-model ratio, not measured DRAM traffic")

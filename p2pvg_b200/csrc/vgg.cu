@@ -125,6 +125,121 @@ __global__ void upsample2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ d
   }
 }
 
+// ---- 16-byte-vector versions (C a multiple of the vector width, < 2^31 vectors): one thread per (pixel, channel vector),
+// 32-bit index arithmetic.  The scalar kernels above remain for odd channel counts (the 1/3-channel ends).
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned total, int H, int W, int CV) {
+  constexpr int V = VecN<T>::N;
+  const unsigned Ho = H / 2, Wo = W / 2;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned cv = idx % CV, p = idx / CV;
+    const unsigned xo = p % Wo, q = p / Wo, yo = q % Ho, n = q / Ho;
+    const long long base = ((((long long)n * H + 2 * yo) * W + 2 * xo) * CV + cv) * V;
+    const long long dxo = (long long)CV * V, dyo = (long long)W * CV * V;
+    float a[V], b[V], c[V], d[V];
+    unpack16<T>(ld_raw16(x + base), a);
+    unpack16<T>(ld_raw16(x + base + dxo), b);
+    unpack16<T>(ld_raw16(x + base + dyo), c);
+    unpack16<T>(ld_raw16(x + base + dyo + dxo), d);
+#pragma unroll
+    for (int j = 0; j < V; j++) a[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
+    st_raw16(y + (long long)idx * V, pack16<T>(a));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, unsigned total,
+                                                               int H, int W, int CV) {
+  constexpr int V = VecN<T>::N;
+  const unsigned Ho = H / 2, Wo = W / 2;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned cv = idx % CV, p = idx / CV;
+    const unsigned xo = p % Wo, q = p / Wo, yo = q % Ho, n = q / Ho;
+    const long long base = ((((long long)n * H + 2 * yo) * W + 2 * xo) * CV + cv) * V;
+    const long long off[4] = {0, (long long)CV * V, (long long)W * CV * V, (long long)W * CV * V + (long long)CV * V};
+    float v[4][V], g[V], o[4][V];
+#pragma unroll
+    for (int k = 0; k < 4; k++) unpack16<T>(ld_raw16(x + base + off[k]), v[k]);
+    unpack16<T>(ld_raw16(dy + (long long)idx * V), g);
+#pragma unroll
+    for (int j = 0; j < V; j++) {   // first maximum in row-major order (torch's tie rule)
+      int best = 0;
+      float bv = v[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; k++)
+        if (v[k][j] > bv) { bv = v[k][j]; best = k; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k][j] = (k == best) ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) st_raw16(dx + base + off[k], pack16<T>(o[k]));
+  }
+}
+
+// one thread per INPUT pixel vector: read once, write the 2x2 replicas
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned total, int H, int W, int CV) {
+  constexpr int V = VecN<T>::N;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned cv = idx % CV, p = idx / CV;
+    const unsigned xi = p % W, q = p / W, yi = q % H, n = q / H;
+    const uint4 v = ld_raw16(x + (long long)idx * V);
+    const long long base = ((((long long)n * 2 * H + 2 * yi) * (2 * W) + 2 * xi) * CV + cv) * V;
+    const long long dxo = (long long)CV * V, dyo = 2LL * W * CV * V;
+    st_raw16(y + base, v);
+    st_raw16(y + base + dxo, v);
+    st_raw16(y + base + dyo, v);
+    st_raw16(y + base + dyo + dxo, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_bwd_vec_kernel(const T* __restrict__ dy, T* __restrict__ dx, unsigned total, int H, int W, int CV) {
+  constexpr int V = VecN<T>::N;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned cv = idx % CV, p = idx / CV;
+    const unsigned xi = p % W, q = p / W, yi = q % H, n = q / H;
+    const long long base = ((((long long)n * 2 * H + 2 * yi) * (2 * W) + 2 * xi) * CV + cv) * V;
+    const long long dxo = (long long)CV * V, dyo = 2LL * W * CV * V;
+    float a[V], b[V], c[V], d[V];
+    unpack16<T>(ld_raw16(dy + base), a);
+    unpack16<T>(ld_raw16(dy + base + dxo), b);
+    unpack16<T>(ld_raw16(dy + base + dyo), c);
+    unpack16<T>(ld_raw16(dy + base + dyo + dxo), d);
+#pragma unroll
+    for (int j = 0; j < V; j++) a[j] = (a[j] + b[j]) + (c[j] + d[j]);
+    st_raw16(dx + (long long)idx * V, pack16<T>(a));
+  }
+}
+
+// 3x3 lowering of a few-channel map (9 C <= 32, row pitch 32): one thread per output ROW (pixel) -- 27 scalar gathers, then
+// the whole 32-element row (zero padded) goes out as 16-byte vectors (the scalar kernel spent a 64-bit division per element)
+template <typename T, int C>
+__global__ void __launch_bounds__(256) im2col3_row32_kernel(const T* __restrict__ x, T* __restrict__ col, unsigned npix, int H, int W, int sgn) {
+  constexpr int V = VecN<T>::N;
+  for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const unsigned xx = pix % W, q = pix / W, yy = q % H, n = q / H;
+    float row[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) row[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++) {
+      const int sy = (int)yy + sgn * (kh - 1);
+#pragma unroll
+      for (int kw = 0; kw < 3; kw++) {
+        const int sx = (int)xx + sgn * (kw - 1);
+        if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+        const T* src = x + (((long long)n * H + sy) * W + sx) * C;
+#pragma unroll
+        for (int c = 0; c < C; c++) row[(kh * 3 + kw) * C + c] = ld_f(src + c);
+      }
+    }
+    T* dst = col + (long long)pix * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += V) st_raw16(dst + j, pack16<T>(row + j));
+  }
+}
+
 // dst[g*n + i] += src[grp_src[g]*n + i]   (fp32 addend shared by the groups that reuse a skip frame)
 template <typename T>
 __global__ void gather_add_kernel(T* __restrict__ dst, const float* __restrict__ src, const int* __restrict__ grp_src, int G, long long n) {
@@ -135,12 +250,26 @@ __global__ void gather_add_kernel(T* __restrict__ dst, const float* __restrict__
   }
 }
 
+// 16-byte vector path: channels a multiple of the vector width, 16-byte aligned tensors, fewer than 2^31 vectors
+inline bool vec_ok(int dtype, int C, long long total, const void* a, const void* b, const void* c) {
+  const int V = dtype == P2PVG_BF16 ? 8 : 4;
+  return C % V == 0 && total / V < (1LL << 31) &&
+         ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
 }  // namespace
 
 int p2pvg_im2col3_impl(const void* x, void* col, int dtype, int N, int H, int W, int C, int ld, int sgn, cudaStream_t st) {
   P2PVG_REQUIRE(ld >= 9 * C, P2PVG_ERR_BAD_ARG, "im2col3: ld %d < 9*C", ld);
   if (N == 0) return P2PVG_OK;
   const long long total = (long long)N * H * W * ld;
+  if (ld == 32 && (C == 1 || C == 3) && (long long)N * H * W < (1LL << 31) && (reinterpret_cast<uintptr_t>(col) & 15) == 0) {
+    const unsigned npix = (unsigned)((long long)N * H * W);
+    const int sg = sgn < 0 ? -1 : 1;
+    if (C == 3) { DISPATCH_DTYPE(dtype, T, (im2col3_row32_kernel<T, 3><<<grid_for(npix, 256), 256, 0, st>>>((const T*)x, (T*)col, npix, H, W, sg))); }
+    else { DISPATCH_DTYPE(dtype, T, (im2col3_row32_kernel<T, 1><<<grid_for(npix, 256), 256, 0, st>>>((const T*)x, (T*)col, npix, H, W, sg))); }
+    return p2pvg_check_launch("im2col3");
+  }
   DISPATCH_DTYPE(dtype, T, (im2col3_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, ld, sgn < 0 ? -1 : 1)));
   return p2pvg_check_launch("im2col3");
 }
@@ -157,6 +286,12 @@ int p2pvg_maxpool2_fwd_impl(const void* x, void* y, int dtype, int N, int H, int
   P2PVG_REQUIRE(H % 2 == 0 && W % 2 == 0, P2PVG_ERR_BAD_ARG, "maxpool2: odd map %dx%d", H, W);
   if (N == 0) return P2PVG_OK;
   const long long total = (long long)N * (H / 2) * (W / 2) * C;
+  if (vec_ok(dtype, C, total, x, y, nullptr)) {
+    const int V = dtype == P2PVG_BF16 ? 8 : 4;
+    const unsigned tv = (unsigned)(total / V);
+    DISPATCH_DTYPE(dtype, T, (maxpool2_fwd_vec_kernel<T><<<grid_for(tv, 256), 256, 0, st>>>((const T*)x, (T*)y, tv, H, W, C / V)));
+    return p2pvg_check_launch("maxpool2_fwd");
+  }
   DISPATCH_DTYPE(dtype, T, (maxpool2_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C)));
   return p2pvg_check_launch("maxpool2_fwd");
 }
@@ -165,6 +300,12 @@ int p2pvg_maxpool2_bwd_impl(const void* x, const void* dy, void* dx, int dtype, 
   P2PVG_REQUIRE(H % 2 == 0 && W % 2 == 0, P2PVG_ERR_BAD_ARG, "maxpool2: odd map %dx%d", H, W);
   if (N == 0) return P2PVG_OK;
   const long long total = (long long)N * (H / 2) * (W / 2) * C;
+  if (vec_ok(dtype, C, total, x, dy, dx)) {
+    const int V = dtype == P2PVG_BF16 ? 8 : 4;
+    const unsigned tv = (unsigned)(total / V);
+    DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_vec_kernel<T><<<grid_for(tv, 256), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, tv, H, W, C / V)));
+    return p2pvg_check_launch("maxpool2_bwd");
+  }
   DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, N, H, W, C)));
   return p2pvg_check_launch("maxpool2_bwd");
 }
@@ -172,6 +313,12 @@ int p2pvg_maxpool2_bwd_impl(const void* x, const void* dy, void* dx, int dtype, 
 int p2pvg_upsample2_fwd_impl(const void* x, void* y, int dtype, int N, int H, int W, int C, cudaStream_t st) {
   if (N == 0) return P2PVG_OK;
   const long long total = (long long)N * 4 * H * W * C;
+  if (vec_ok(dtype, C, total / 4, x, y, nullptr)) {
+    const int V = dtype == P2PVG_BF16 ? 8 : 4;
+    const unsigned tv = (unsigned)(total / 4 / V);
+    DISPATCH_DTYPE(dtype, T, (upsample2_fwd_vec_kernel<T><<<grid_for(tv, 256), 256, 0, st>>>((const T*)x, (T*)y, tv, H, W, C / V)));
+    return p2pvg_check_launch("upsample2_fwd");
+  }
   DISPATCH_DTYPE(dtype, T, (upsample2_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C)));
   return p2pvg_check_launch("upsample2_fwd");
 }
@@ -179,6 +326,12 @@ int p2pvg_upsample2_fwd_impl(const void* x, void* y, int dtype, int N, int H, in
 int p2pvg_upsample2_bwd_impl(const void* dy, void* dx, int dtype, int N, int H, int W, int C, cudaStream_t st) {
   if (N == 0) return P2PVG_OK;
   const long long total = (long long)N * H * W * C;
+  if (vec_ok(dtype, C, total, dy, dx, nullptr)) {
+    const int V = dtype == P2PVG_BF16 ? 8 : 4;
+    const unsigned tv = (unsigned)(total / V);
+    DISPATCH_DTYPE(dtype, T, (upsample2_bwd_vec_kernel<T><<<grid_for(tv, 256), 256, 0, st>>>((const T*)dy, (T*)dx, tv, H, W, C / V)));
+    return p2pvg_check_launch("upsample2_bwd");
+  }
   DISPATCH_DTYPE(dtype, T, (upsample2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C)));
   return p2pvg_check_launch("upsample2_bwd");
 }
