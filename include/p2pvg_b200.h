@@ -85,7 +85,7 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
  *   kind 5: kind 3 with mirrored tap offsets, b = [Cin,(kh,kw,Cout)]                          data gradient
  * Returns P2PVG_ERR_UNSUPPORTED for shapes outside the pixel-box tiling (channels not a multiple of 64, ...). */
 int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c, int c_dtype, int64_t ldc, int N, int H, int W, int Ck,
-                    int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
+                    int Cn, int Cm, const float* bias, const void* addend, const int* grp_src, int imgs_per_group, int accumulate,
                     void* workspace, size_t ws_bytes, const struct p2pvg_conv_fusion* fusion, void* stream);
 
 /* Optional epilogue fusions of p2pvg_conv_gemm (kinds 0, 2, 3, 5; `fusion` may be NULL, every member may be NULL).
@@ -96,7 +96,8 @@ int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c
  *                     (sum y, sum y^2) of the tile's rows, y as stored (bf16-rounded for a bf16 output).  The tile of GEMM
  *                     row block mt and phase ph is row mt*phases + ph; reduce per group with p2pvg_bn_fwd_finalize_tiles
  *                     (rows of one BatchNorm group must be a multiple of 128).
- *   bwd_*             reserved for the BatchNorm-backward reduction of a data-gradient GEMM (sum dz, sum dz*xhat). */
+ *   bwd_*             reserved for the BatchNorm-backward reduction of a data-gradient GEMM (sum dz, sum dz*xhat).
+ *   addend_dtype      the skip-half addend may be stored in bf16 (it is the output of another p2pvg_conv_gemm call). */
 typedef struct p2pvg_conv_fusion {
   void* fwd_stat_partial;
   const void* bwd_raw;
@@ -106,6 +107,7 @@ typedef struct p2pvg_conv_fusion {
   const float* bwd_shift;
   void* bwd_stat_partial;
   int64_t rows_per_group;
+  int addend_dtype; /* dtype of `addend`: P2PVG_F32 (default, also without a fusion struct) or P2PVG_BF16 (half the epilogue read traffic) */
 } p2pvg_conv_fusion_t;
 
 /* vgg_64 data movement (models/vgg_64.py), NHWC, dtype f32 | bf16.

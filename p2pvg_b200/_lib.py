@@ -62,7 +62,7 @@ class ConvFusion(ctypes.Structure):
     """p2pvg_conv_fusion_t (include/p2pvg_b200.h)."""
     _fields_ = [("fwd_stat_partial", ctypes.c_void_p), ("bwd_raw", ctypes.c_void_p), ("bwd_mean", ctypes.c_void_p),
                 ("bwd_invstd", ctypes.c_void_p), ("bwd_scale", ctypes.c_void_p), ("bwd_shift", ctypes.c_void_p),
-                ("bwd_stat_partial", ctypes.c_void_p), ("rows_per_group", ctypes.c_int64)]
+                ("bwd_stat_partial", ctypes.c_void_p), ("rows_per_group", ctypes.c_int64), ("addend_dtype", ctypes.c_int)]
 
 
 class _Workspaces:
@@ -178,8 +178,9 @@ class CudaKernels:
             ldc = taps * Cn if kind in (1, 4) else Cn
         ws = self.gemm_workspace()
         fusion = None
-        if stat_partial is not None:
-            fusion = ctypes.byref(ConvFusion(fwd_stat_partial=stat_partial.data_ptr()))
+        if stat_partial is not None or (addend is not None and addend.dtype == torch.bfloat16):
+            fusion = ctypes.byref(ConvFusion(fwd_stat_partial=stat_partial.data_ptr() if stat_partial is not None else None,
+                                             addend_dtype=_dt(addend) if addend is not None else F32))
         self._ck(self.lib.p2pvg_conv_gemm(_i(kind), _p(a), _p(b), _i64(ldb), _p(c), _i(_dt(c)), _i64(ldc), _i(N), _i(H), _i(W), _i(Ck),
                                           _i(Cn), _i(Cm), _p(bias), _p(addend), _p(grp_src), _i(imgs_per_group), _i(int(accumulate)),
                                           _p(ws), _sz(ws.numel()), fusion, self._stream()))

@@ -43,7 +43,7 @@ int p2pvg_conv_thin_in_impl(const void*, int, const float*, const float*, void*,
 int p2pvg_convT_thin_out_impl(const void*, int, const float*, const float*, const float*, const int*, int, void*, int, int, int, int, int,
                               int, cudaStream_t);
 int p2pvg_conv_gemm_impl(int, const void*, const void*, long long, void*, int, long long, int, int, int, int, int, int, const float*,
-                         const float*, const int*, int, int, void*, size_t, void*, cudaStream_t);
+                         const float*, const int*, int, int, void*, size_t, void*, int, cudaStream_t);
 int p2pvg_bn_fwd_finalize_tiles_impl(const void*, int, int, int, int, long long, int, const float*, const float*, float, float*, float*, float*,
                                      float*, float*, cudaStream_t);
 int p2pvg_bn_bwd_finalize_tiles_impl(const void*, int, int, int, int, int, float*, float*, cudaStream_t);
@@ -145,14 +145,16 @@ int p2pvg_gemm(const void* A, int in_dtype, int a_mn, int64_t lda, const void* B
 }
 
 int p2pvg_conv_gemm(int kind, const void* a, const void* b, int64_t ldb, void* c, int c_dtype, int64_t ldc, int N, int H, int W, int Ck,
-                    int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group, int accumulate,
+                    int Cn, int Cm, const float* bias, const void* addend, const int* grp_src, int imgs_per_group, int accumulate,
                     void* workspace, size_t ws_bytes, const p2pvg_conv_fusion_t* fusion, void* stream) {
   P2PVG_REQUIRE(a && b && c, P2PVG_ERR_BAD_ARG, "conv_gemm: null operand");
   void* fwd_stat = fusion ? fusion->fwd_stat_partial : nullptr;
   P2PVG_REQUIRE(!fusion || fusion->bwd_stat_partial == nullptr, P2PVG_ERR_UNSUPPORTED, "conv_gemm: backward BatchNorm fusion is reserved");
   P2PVG_REQUIRE(!(fwd_stat && accumulate), P2PVG_ERR_BAD_ARG, "conv_gemm: statistics of an accumulating GEMM are not defined");
-  return p2pvg_conv_gemm_impl(kind, a, b, ldb, c, c_dtype, ldc, N, H, W, Ck, Cn, Cm, bias, addend, grp_src, imgs_per_group, accumulate,
-                              workspace, ws_bytes, fwd_stat, ST);
+  const int add_dt = fusion ? fusion->addend_dtype : P2PVG_F32;
+  P2PVG_REQUIRE(add_dt == P2PVG_F32 || add_dt == P2PVG_BF16, P2PVG_ERR_BAD_ARG, "conv_gemm: bad addend dtype %d", add_dt);
+  return p2pvg_conv_gemm_impl(kind, a, b, ldb, c, c_dtype, ldc, N, H, W, Ck, Cn, Cm, bias, reinterpret_cast<const float*>(addend), grp_src,
+                              imgs_per_group, accumulate, workspace, ws_bytes, fwd_stat, add_dt, ST);
 }
 
 int p2pvg_conv_thin_in(const void* x, int dtype, const float* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,

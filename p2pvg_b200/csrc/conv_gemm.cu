@@ -45,6 +45,7 @@ struct Geom {
   int bh64, bn64;       // pixel box of 64 pixels (kind 1 K-blocks): {bw64, bh64, bn64}; bw64 = 64 < W for 128-wide maps
   int bw64;
   int imgs_per_group;   // addend indexing
+  int add_bf16;         // the addend tensor is bf16 (half the epilogue read traffic of the fp32 form)
   int ks, st, sgn;      // filter taps per side (4 | 3), stride between the two maps (2 | 1), tap-offset sign (+1 | -1)
 };
 
@@ -57,6 +58,41 @@ __device__ __forceinline__ void pix_block(int pb, int P, int H, int W, int bh, i
   } else {
     n0 = pb * bn;
     y0 = 0;
+  }
+}
+
+// 64 addend columns of one output row into 16-byte registers: 16 loads for fp32, 8 for bf16
+__device__ __forceinline__ void addend_load64(float4 (&a4)[16], const float* base, long long elem_off, bool is_bf16) {
+  if (is_bf16) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem_off);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint4 r = p[j];
+      a4[j] = make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(base + elem_off);
+#pragma unroll
+    for (int j = 0; j < 16; j++) a4[j] = p[j];
+  }
+}
+// f[0..31] += columns [32 h, 32 h + 32) of what addend_load64 fetched
+__device__ __forceinline__ void addend_add32(float (&f)[32], const float4 (&a4)[16], int h, bool is_bf16) {
+  if (is_bf16) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float4 r = a4[4 * h + j];
+      float v[8];
+      unpack16<bf16>(make_uint4(__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w)), v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) f[8 * j + i] += v[i];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float4 x4 = a4[8 * h + j];
+      f[4 * j] += x4.x; f[4 * j + 1] += x4.y; f[4 * j + 2] += x4.z; f[4 * j + 3] += x4.w;
+    }
   }
 }
 
@@ -280,12 +316,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         epi_bar_sync();
       }
       const bool use_add = (KIND != 1) && addend != nullptr && row_ok;
-      const float* arow0 = use_add ? addend + add_row * g.Ntot + n0 : nullptr;
-      float4 a4[16];  // fp32 addend of the next 64 columns, requested before the accumulator is waited for
-      if (use_add) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(arow0 + 4 * j);
-      }
+      const long long aoff0 = add_row * g.Ntot + n0;   // element offset of this row's first addend column
+      const bool abf = g.add_bf16 != 0;
+      float4 a4[16];  // addend of the next 64 columns, requested before the accumulator is waited for
+      if (use_add) addend_load64(a4, addend, aoff0, abf);
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -296,10 +330,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(pr * 64);
         tmem_ld32(taddr, v2);
         tmem_ld32(taddr + 32, v2 + 32);
-        if (pr > 0 && use_add) {
-#pragma unroll
-          for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(arow0 + pr * 64 + 4 * j);
-        }
+        if (pr > 0 && use_add) addend_load64(a4, addend, aoff0 + pr * 64, abf);
         tmem_ld_wait_dep(v2);
         tmem_ld_wait_dep(v2 + 32);
         if (pr == BN / 64 - 1) {
@@ -332,13 +363,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
-          if (use_add) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float4 x4 = a4[8 * h + j];
-              f[4 * j] += x4.x; f[4 * j + 1] += x4.y; f[4 * j + 2] += x4.z; f[4 * j + 3] += x4.w;
-            }
-          }
+          if (use_add) addend_add32(f, a4, h, abf);
           if (STAT) {
             // statistics of the tensor AS STORED (bf16-rounded when the output is bf16); all 32 lanes take part
             float s1[32], s2[32];
@@ -592,12 +617,10 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       epi_bar_sync();   // every warp is done with bias_s of the previous tile
       if (rt < 64) bias_s[rt] = (bias != nullptr) ? bias[n0 + rt] : 0.f;
       epi_bar_sync();
+      const bool abf = g.add_bf16 != 0;
       float4 a4[16];
-      if (use_add) {   // skip addend of phase 0, requested before the accumulator is waited for
-        const float* ar = addend + (((long long)n2 * (2 * g.H) + 2 * y) * (2 * g.W) + 2 * xx) * g.Cn + n0;
-#pragma unroll
-        for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(ar + 4 * j);
-      }
+      if (use_add)   // skip addend of the first column block's phase (p0), requested before the accumulator is waited for
+        addend_load64(a4, addend, (((long long)n2 * (2 * g.H) + 2 * y) * (2 * g.W) + 2 * xx) * g.Cn + n0, abf);
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -609,11 +632,7 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(cbi * 64);
         tmem_ld32(taddr, v2);
         tmem_ld32(taddr + 32, v2 + 32);
-        if (cbi > 0 && use_add) {
-          const float* ar = addend + (((long long)n2 * (2 * g.H) + oy) * (2 * g.W) + ox) * g.Cn + n0;
-#pragma unroll
-          for (int j = 0; j < 16; j++) a4[j] = *reinterpret_cast<const float4*>(ar + 4 * j);
-        }
+        if (cbi > 0 && use_add) addend_load64(a4, addend, (((long long)n2 * (2 * g.H) + oy) * (2 * g.W) + ox) * g.Cn + n0, abf);
         tmem_ld_wait_dep(v2);
         tmem_ld_wait_dep(v2 + 32);
         if (cbi == 3) {   // the accumulator goes back to the MMA warp before the last stores
@@ -631,13 +650,7 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
             f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
-          if (use_add) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float4 x4 = a4[8 * h + j];
-              f[4 * j] += x4.x; f[4 * j + 1] += x4.y; f[4 * j + 2] += x4.z; f[4 * j + 3] += x4.w;
-            }
-          }
+          if (use_add) addend_add32(f, a4, h, abf);
           if (STAT) {
             float s1[32], s2[32];
 #pragma unroll
@@ -832,7 +845,7 @@ int launch_convt4(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_d
 // fit the pixel-box tiling (the caller then uses the explicit im2col / col2im path).
 int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, void* c, int c_dtype, long long ldc, int N, int H, int W,
                          int Ck, int Cn, int Cm, const float* bias, const float* addend, const int* grp_src, int imgs_per_group,
-                         int accumulate, void* ws, size_t ws_bytes, void* stat_partial_v, cudaStream_t st) {
+                         int accumulate, void* ws, size_t ws_bytes, void* stat_partial_v, int addend_dtype, cudaStream_t st) {
   float2* stat_partial = reinterpret_cast<float2*>(stat_partial_v);
   std::call_once(g_once2, resolve2);
   P2PVG_REQUIRE(g_enc != nullptr, P2PVG_ERR_UNSUPPORTED, "conv_gemm: cuTensorMapEncodeTiled unavailable");
@@ -840,6 +853,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   if (N <= 0) return P2PVG_OK;
   Geom g;
   g.N = N; g.H = H; g.W = W; g.Ck = Ck; g.Cn = Cn; g.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : 1;
+  g.add_bf16 = (addend != nullptr && addend_dtype == P2PVG_BF16) ? 1 : 0;
   g.ks = kind >= 3 ? 3 : 4; g.st = kind >= 3 ? 1 : 2; g.sgn = kind == 5 ? -1 : 1;
   const int taps = g.ks * g.ks;
   if (kind == 3 || kind == 5) kind = 0;

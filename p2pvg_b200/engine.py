@@ -191,6 +191,9 @@ class TrainEngine:
         # BatchNorm forward statistics come out of the producing implicit GEMM's epilogue (per-tile column sums) instead of a
         # separate pass over the stored tensor; P2PVG_BN_FUSE=0 keeps the stand-alone statistics kernel (A/B comparison)
         # 1-channel stacks: tap gather + sigmoid + MSE of the last decoder layer as one kernel (no raw-output tensor)
+        # the skip-half addend of the implicit (transposed) convolutions is stored in the activation dtype: it is read once per
+        # decode call by the main GEMM's epilogue (fp32 doubled that traffic and its L2 footprint); P2PVG_ADDEND_BF16=0 = fp32
+        self.addend_dtype = act_dtype if os.environ.get("P2PVG_ADDEND_BF16", "1") != "0" else torch.float32
         self.fuse_last = hasattr(kernels, "convt_c1_loss") and act_dtype == torch.bfloat16 and os.environ.get("P2PVG_FUSE_LAST", "1") != "0"
         self.fuse_stats = self.implicit and os.environ.get("P2PVG_BN_FUSE", "1") != "0"
         # ... but only where the tile's MMA time hides the extra epilogue work: reduction length x tile width of the GEMM must
@@ -781,7 +784,7 @@ class TrainEngine:
             sp = rec_fused = None
             if imp:
                 # skip half once per distinct source frame (fp32, bias folded in), added in the epilogue of the main GEMM
-                addS = self.fbuf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout)
+                addS = self.buf(f"dec_addS{k}", nskip * B * 4 * Hi * Hi * cout, self.addend_dtype)
                 K.conv_gemm(2, skip, wS, addS, nskip * B, Hi, Hi, cd, cout, bias=P[cn + ".bias"])
                 sp = self.stat_buf(f"dec{k}", Md, 4, cout, B * Hi * Hi, kred=4 * cd) if k < n - 1 else None
                 K.conv_gemm(2, d, wD, raw, N, Hi, Hi, cd, cout, addend=addS, grp_src=self.ix["skip_src"], imgs_per_group=B,

@@ -61,6 +61,12 @@ def test_kind2_conv_transpose_s2(K, N, H, Ck, Cn):
     K.conv_gemm(2, nhwc(x), wp, outb, N, H, H, Ck, Cn, bias=bias, addend=addend, grp_src=src, imgs_per_group=B)
     want = nhwc(ref) + addend[idx]
     assert (outb.float() - want).abs().max().item() <= 2e-2 * want.abs().max().item() + 1e-2
+    # the same with the addend stored in bf16 (p2pvg_conv_fusion.addend_dtype)
+    add16 = addend.bfloat16()
+    outc = torch.empty_like(outb)
+    K.conv_gemm(2, nhwc(x), wp, outc, N, H, H, Ck, Cn, bias=bias, addend=add16, grp_src=src, imgs_per_group=B)
+    want16 = nhwc(ref) + add16.float()[idx]
+    assert (outc.float() - want16).abs().max().item() <= 2e-2 * want16.abs().max().item() + 1e-2
 
 
 @pytest.mark.parametrize("N,H,Cm,Cn", [(5, 8, 128, 64), (3, 4, 64, 128), (2, 16, 64, 64), (64, 4, 512, 256), (40, 8, 256, 128), (9, 32, 64, 64)])
