@@ -395,7 +395,11 @@ def main():
     roof = roof_lstm = phases = None
     if rank == 0:
         np.random.seed(0)
-        eng.step(x_dev, use_graph=False, return_device=True)   # plan of the measured pattern for the instrumented passes
+        saved_dist, eng.dist = eng.dist, None   # everything below is a rank-0-only measurement: no collectives
+        try:
+            eng.step(x_dev, use_graph=False, return_device=True)   # plan of the measured pattern for the instrumented passes
+        finally:
+            eng.dist = saved_dist
         S_meas = eng.last_plan.S
     # ---- roofline of the tensor-core kernels: instrumented eager pass ------------------------------
     if rank == 0 and args.precision == "bf16" and not pose:
