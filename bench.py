@@ -490,7 +490,7 @@ def main():
             lib = dict(unavailable=repr(e)[:200])
     # ---- CPU baseline (oracle port) on the host cores: bounded sample -------------------------------
     cpu = None
-    if rank == 0 and not args.skip_cpu:
+    if rank == 0 and world == 1 and not args.skip_cpu:   # reported at N = 1 only (the contract): bounded sample on the host cores
         if all_cpus:
             os.sched_setaffinity(0, all_cpus)
         cpu, _ = cpu_baseline(c, T, args.skip_prob, 2, 1)
