@@ -46,6 +46,8 @@ struct Geom {
   int bw64;
   int imgs_per_group;   // addend indexing
   int add_bf16;         // the addend tensor is bf16 (half the epilogue read traffic of the fp32 form)
+  int swap;             // kind 1 with the operand roles swapped: M = taps*Cn (gathered map), N = Cm (few output channels would waste
+                        // half of a 128-row MMA tile otherwise); the partial sums are [taps*Cn][Cm] and the reduce kernel transposes
   int ks, st, sgn;      // filter taps per side (4 | 3), stride between the two maps (2 | 1), tap-offset sign (+1 | -1)
 };
 
@@ -167,6 +169,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int kn0 = 0, ky0 = 0, kx0 = 0;
         int t_kh = 0, t_kw = 0, t_cc = 0;
         int qc0[BN / 64], qdx[BN / 64], qdy[BN / 64];
+        int mc0[2] = {0, 0}, mdx[2] = {0, 0}, mdy[2] = {0, 0};
         if (KIND == 1) {
           if (g.bw64 < g.W) {  // a 64-pixel K-block is a fraction of one row
             const int per_row = g.W / g.bw64;
@@ -185,6 +188,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             qc0[q] = nb - tap * g.Cn;
             qdx[q] = tap - kh * g.ks - 1;
             qdy[q] = kh - 1;
+          }
+          if (g.swap) {   // the gathered map is the A operand: (tap, channel) of the two 64-row halves of the M tile
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+              const int mb = mt * BLOCK_M + 64 * q;
+              int tap = mb / g.Cn;
+              if (tap >= g.ks * g.ks) tap = g.ks * g.ks - 1;   // rows past M are discarded by the epilogue: any in-bounds tap will do
+              const int kh = tap / g.ks;
+              mc0[q] = mb < g.M ? mb - tap * g.Cn : 0;
+              mdx[q] = tap - kh * g.ks - 1;
+              mdy[q] = kh - 1;
+            }
           }
         }
         for (int kb = kb0; kb < kb1; kb++, it++) {
@@ -212,11 +227,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d(&tmB, &full_bar[s], sb + q * 64 * 128, (ky * 4 + kx) * g.Cn + n0 + 64 * q, c0);
           } else {
             const int m0 = mt * BLOCK_M;
-            tma_load_2d(&tmA, &full_bar[s], sa, m0, kb * 64);
-            tma_load_2d(&tmA, &full_bar[s], sa + 64 * 128, m0 + 64, kb * 64);
+            if (g.swap) {
+              tma_load_4d(&tmA, &full_bar[s], sa, mc0[0], g.st * kx0 + mdx[0], g.st * ky0 + mdy[0], kn0);
+              tma_load_4d(&tmA, &full_bar[s], sa + 64 * 128, mc0[1], g.st * kx0 + mdx[1], g.st * ky0 + mdy[1], kn0);
 #pragma unroll
-            for (int q = 0; q < BN / 64; q++)
-              tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, qc0[q], g.st * kx0 + qdx[q], g.st * ky0 + qdy[q], kn0);
+              for (int q = 0; q < BN / 64; q++) tma_load_2d(&tmB, &full_bar[s], sb + q * 64 * 128, n0 + 64 * q, kb * 64);
+            } else {
+              tma_load_2d(&tmA, &full_bar[s], sa, m0, kb * 64);
+              tma_load_2d(&tmA, &full_bar[s], sa + 64 * 128, m0 + 64, kb * 64);
+#pragma unroll
+              for (int q = 0; q < BN / 64; q++)
+                tma_load_4d(&tmB, &full_bar[s], sb + q * 64 * 128, qc0[q], g.st * kx0 + qdx[q], g.st * ky0 + qdy[q], kn0);
+            }
             // next 64-pixel box
             if (g.bw64 < g.W) {
               kx0 += g.bw64;
@@ -697,14 +719,16 @@ convt4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
+// C[M, N] = sum_z partial[z]; transposed != 0: the partials are [z][N][M] (kind 1 with swapped operand roles)
 __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ C, long long ldc, int M, int N,
-                                          int accumulate) {
+                                          int accumulate, int transposed) {
   const long long total = (long long)M * N;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long m = idx / N;
     const int n = (int)(idx - m * N);
+    const long long pidx = transposed ? (long long)n * M + m : idx;
     float acc = 0.f;
-    for (int z = 0; z < splits; z++) acc += partial[(long long)z * total + idx];
+    for (int z = 0; z < splits; z++) acc += partial[(long long)z * total + pidx];
     if (accumulate) acc += C[m * ldc + n];
     C[m * ldc + n] = acc;
   }
@@ -723,6 +747,7 @@ int g_convt4_max_cn = 64;   // kind 2 with at most this many output channels: th
                             // 0 = off).  Measured (C2 step, B200): 64 -> -0.36 ms; 128 -> +0.1 ms (the N = 64 MMAs of the fused tile issue twice as
                             // many instructions as the 128-wide phase tiles, which outweighs the saved operand fills)
 int g_convt4_attr[2] = {};
+int g_k1_swap = 1;   // kind 1 / 4 with 64 output channels: swapped operand roles (P2PVG_K1_SWAP=0 disables)
 
 void resolve2() {
   int dev = 0, sms = 0;
@@ -734,6 +759,8 @@ void resolve2() {
   (void)cudaGetLastError();
   const char* e = getenv("P2PVG_CONV_BN256");
   if (e != nullptr && e[0] == '0') g_bn256 = 0;
+  const char* sw = getenv("P2PVG_K1_SWAP");
+  if (sw != nullptr && sw[0] == '0') g_k1_swap = 0;
   const char* f4 = getenv("P2PVG_CONVT4_MAX_CN");
   if (f4 != nullptr) g_convt4_max_cn = atoi(f4);
   const char* w = getenv("P2PVG_K1_WIDE_MAX");
@@ -854,6 +881,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   Geom g;
   g.N = N; g.H = H; g.W = W; g.Ck = Ck; g.Cn = Cn; g.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : 1;
   g.add_bf16 = (addend != nullptr && addend_dtype == P2PVG_BF16) ? 1 : 0;
+  g.swap = 0;
   g.ks = kind >= 3 ? 3 : 4; g.st = kind >= 3 ? 1 : 2; g.sgn = kind == 5 ? -1 : 1;
   const int taps = g.ks * g.ks;
   if (kind == 3 || kind == 5) kind = 0;
@@ -909,28 +937,41 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   // kind 1: weight gradient
   P2PVG_REQUIRE(c_dtype == P2PVG_F32, P2PVG_ERR_BAD_ARG, "conv_gemm kind 1 writes fp32");
   P2PVG_REQUIRE(stat_partial == nullptr, P2PVG_ERR_BAD_ARG, "conv_gemm: BatchNorm statistics belong to the forward / data-gradient kinds");
-  g.M = Cm; g.Ntot = taps * Cn; g.Ck = 64;
-  rc = map2d(&ta, a, Cm, pix, Cm, 64);  // a_small [pix][Cm] as MN-major A
-  if (rc) return rc;
-  rc = map4d(&tb, b, N, g.st * H, g.st * W, Cn, g.bw64, g.bh64, g.bn64, g.st);
-  if (rc) return rc;
-  // a wide tile spans several filter taps when Cn == 64; 256-wide tiles pay off while there are few output tiles (measured)
-  const bool wide = g.Ntot % 256 == 0 && g_bn256 && (long long)cdiv(Cm, BLOCK_M) * (g.Ntot / 128) <= g_k1_wide_max;
-  const int BN = wide ? 256 : (g.Ntot % 128 == 0) ? 128 : 64;
+  g.Ck = 64;
+  // 64 output channels would fill only half of a 128-row MMA tile: swap the operand roles (M = taps*Cn from the gathered map,
+  // N = Cm); the partial sums are then [taps*Cn][Cm] and the split-K reduce kernel writes the transposed result
   const int nkb = (int)((pix + 63) / 64);
-  const long long tiles = (long long)cdiv(Cm, BLOCK_M) * cdiv(g.Ntot, BN);
+  g.swap = (Cm == 64 && g_k1_swap && nkb >= 16 && ws != nullptr && (size_t)2 * taps * Cn * Cm * sizeof(float) <= ws_bytes) ? 1 : 0;
+  if (g.swap) {
+    g.M = taps * Cn; g.Ntot = Cm;
+    rc = map4d(&ta, b, N, g.st * H, g.st * W, Cn, g.bw64, g.bh64, g.bn64, g.st);
+    if (rc) return rc;
+    rc = map2d(&tb, a, Cm, pix, Cm, 64);
+    if (rc) return rc;
+  } else {
+    g.M = Cm; g.Ntot = taps * Cn;
+    rc = map2d(&ta, a, Cm, pix, Cm, 64);  // a_small [pix][Cm] as MN-major A
+    if (rc) return rc;
+    rc = map4d(&tb, b, N, g.st * H, g.st * W, Cn, g.bw64, g.bh64, g.bn64, g.st);
+    if (rc) return rc;
+  }
+  // a wide tile spans several filter taps when Cn == 64; 256-wide tiles pay off while there are few output tiles (measured)
+  const bool wide = !g.swap && g.Ntot % 256 == 0 && g_bn256 && (long long)cdiv(Cm, BLOCK_M) * (g.Ntot / 128) <= g_k1_wide_max;
+  const int BN = wide ? 256 : (g.Ntot % 128 == 0) ? 128 : 64;
+  const long long tiles = (long long)cdiv(g.M, BLOCK_M) * cdiv(g.Ntot, BN);
   // split-K chosen by a small cost model (units: time of one 128x128x64 k-block on one SM, ~0.22 us): the persistent grid
   // processes ceil(items / SMs) rounds of (k-blocks per item + fixed per-item cost); partial sums cost a write + read
-  int splits = 1;
+  int splits = g.swap ? 2 : 1;
   {
     double best = 1e300;
     const int maxs = nkb / 8 < 64 ? nkb / 8 : 64;
-    for (int s = 1; s <= (maxs < 1 ? 1 : maxs); s++) {
+    const int smin = g.swap ? 2 : 1;
+    for (int s = smin; s <= (maxs < smin ? smin : maxs); s++) {
       const int kb = cdiv(nkb, s), se = cdiv(nkb, kb);
-      if (se > 1 && (ws == nullptr || (size_t)se * Cm * g.Ntot * sizeof(float) > ws_bytes)) continue;
+      if (se > 1 && (ws == nullptr || (size_t)se * g.M * g.Ntot * sizeof(float) > ws_bytes)) continue;
       const long long rounds = cdiv((long long)tiles * se, g_sms);
       double cost = (double)rounds * (kb + 8.0);
-      if (se > 1) cost += (double)se * Cm * g.Ntot * 8.0 / 6.0e12 / (0.22e-6 * BN / 128);
+      if (se > 1) cost += (double)se * g.M * g.Ntot * 8.0 / 6.0e12 / (0.22e-6 * BN / 128);
       if (cost < best) { best = cost; splits = se; }
     }
   }
@@ -942,10 +983,11 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   else rc = launch<1, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, nullptr, nullptr, nullptr, partial, splits, kbps, st);
   if (rc) return rc;
   if (splits > 1) {
-    long long total = (long long)Cm * g.Ntot;
+    long long total = (long long)Cm * taps * Cn;
     int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
-    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, (float*)c, ldc, Cm, g.Ntot, accumulate);
+    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, (float*)c, ldc, Cm, taps * Cn, accumulate, g.swap);
     return p2pvg_check_launch("conv_splitk_reduce");
   }
+  P2PVG_REQUIRE(!g.swap, P2PVG_ERR_UNSUPPORTED, "conv_gemm kind 1 (swapped roles) needs the split-K workspace");
   return P2PVG_OK;
 }
