@@ -233,13 +233,13 @@ int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act
 int p2pvg_mse_chunks(void);
 int p2pvg_sigmoid_mse(const void* raw, int dtype, const float* x, const int* tgt, const float* coef, int G, int64_t E,
                       void* pred, void* d_raw, float* partial, void* stream);
-/* The last decoder layer of the 1-channel dcgan stacks fused with its loss: ConvTranspose2d(2*64, 1, 4, 2, 1) + nn.Sigmoid
- * (models/dcgan_64.py:75-79) + nn.MSELoss against frame tgt[g] (models/p2p_model.py:254,256).  col [G*B*Hi*Wi, 16] / col2
- * [nsrc*B*Hi*Wi, 16]: the 16 tap products of every input pixel of the decoder half / of the shared skip half (group g uses
- * skip source grp_src[g]), as produced by p2pvg_gemm.  Writes d(loss)/d(raw) [G, B*2Hi*2Wi] and the squared-error partials
- * [G, p2pvg_mse_chunks()]; the raw output is never materialised. */
+/* The last decoder layer of the dcgan stacks (C = 1 or 3 image channels) fused with its loss: ConvTranspose2d(2*64, C, 4, 2, 1) +
+ * nn.Sigmoid (models/dcgan_64.py:75-79, models/dcgan_128.py:82-84) + nn.MSELoss against frame tgt[g] (models/p2p_model.py:254,256).
+ * col [G*B*Hi*Wi, 16*C] / col2 [nsrc*B*Hi*Wi, 16*C]: the 16 tap products (x C channels) of every input pixel of the decoder half /
+ * of the shared skip half (group g uses skip source grp_src[g]), as produced by p2pvg_gemm.  Writes d(loss)/d(raw)
+ * [G, B*2Hi*2Wi*C] (NHWC) and the squared-error partials [G, p2pvg_mse_chunks()]; the raw output is never materialised. */
 int p2pvg_convt_c1_loss(const void* col, const void* col2, int dtype, const int* grp_src, const float* bias, const float* x, const int* tgt,
-                        const float* coef, int G, int B, int Hi, int Wi, void* d_raw, float* partial, void* stream);
+                        const float* coef, int G, int B, int Hi, int Wi, int C, void* d_raw, float* partial, void* stream);
 /* h36m pose backbone (models/h36m_mlp.py): nn.LayerNorm of residual_linear (:43,46) forward / backward (fp32, row-wise; dx may alias
  * dy; dgamma == NULL skips the parameter gradients) and the plain nn.MSELoss on [B,17,3] poses (models/p2p_model.py:254,256) with
  * the same partial-sum layout as p2pvg_sigmoid_mse. */

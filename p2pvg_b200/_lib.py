@@ -335,9 +335,9 @@ class CudaKernels:
         self._ck(self.lib.p2pvg_sigmoid_mse(_p(raw), _i(_dt(raw)), _p(x), _p(tgt), _p(coef), _i(G), _i64(E), _p(pred), _p(d_raw),
                                             _p(partial), self._stream()))
 
-    def convt_c1_loss(self, col, col2, grp_src, bias, x, tgt, coef, G, B, Hi, Wi, d_raw, partial):
+    def convt_c1_loss(self, col, col2, grp_src, bias, x, tgt, coef, G, B, Hi, Wi, d_raw, partial, C=1):
         self._ck(self.lib.p2pvg_convt_c1_loss(_p(col), _p(col2), _i(_dt(col)), _p(grp_src), _p(bias), _p(x), _p(tgt), _p(coef), _i(G), _i(B),
-                                              _i(Hi), _i(Wi), _p(d_raw), _p(partial), self._stream()))
+                                              _i(Hi), _i(Wi), _i(C), _p(d_raw), _p(partial), self._stream()))
 
     def layernorm_fwd(self, x, gamma, beta, y, mean, rstd, rows, C, eps=1e-5):
         self._ck(self.lib.p2pvg_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _i64(rows), _i(C), _f(eps), self._stream()))

@@ -98,7 +98,7 @@ int p2pvg_mse_chunks_impl();
 int p2pvg_sigmoid_mse_impl(const void*, int, const float*, const int*, const float*, int, long long, void*, void*, float*, cudaStream_t);
 int p2pvg_finalize_losses_impl(const float*, int, int, double, const float*, float, const float*, int, float, float*, cudaStream_t);
 int p2pvg_convt_c1_loss_impl(const void*, const void*, int, const int*, const float*, const float*, const int*, const float*, int, int, int, int,
-                             void*, float*, cudaStream_t);
+                             int, void*, float*, cudaStream_t);
 int p2pvg_adam_legacy_impl(float*, const float*, float*, float*, long long, double, double, double, double, const int*, cudaStream_t);
 int p2pvg_scale_impl(float*, long long, float, cudaStream_t);
 
@@ -310,9 +310,9 @@ int p2pvg_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act
 }
 int p2pvg_mse_chunks(void) { return p2pvg_mse_chunks_impl(); }
 int p2pvg_convt_c1_loss(const void* col, const void* col2, int dtype, const int* grp_src, const float* bias, const float* x, const int* tgt,
-                        const float* coef, int G, int B, int Hi, int Wi, void* d_raw, float* partial, void* stream) {
+                        const float* coef, int G, int B, int Hi, int Wi, int C, void* d_raw, float* partial, void* stream) {
   P2PVG_REQUIRE(col && col2 && grp_src && x && tgt && coef && d_raw && partial, P2PVG_ERR_BAD_ARG, "convt_c1_loss: null argument");
-  return p2pvg_convt_c1_loss_impl(col, col2, dtype, grp_src, bias, x, tgt, coef, G, B, Hi, Wi, d_raw, partial, ST);
+  return p2pvg_convt_c1_loss_impl(col, col2, dtype, grp_src, bias, x, tgt, coef, G, B, Hi, Wi, C, d_raw, partial, ST);
 }
 int p2pvg_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows, int C,
                         float eps, void* stream) {

@@ -40,40 +40,49 @@ __global__ void __launch_bounds__(256) sigmoid_mse_kernel(const T* __restrict__ 
 // pixel come from the tcgen05 GEMMs (col [N*Hi*Wi, 16] for the decoder path, col2 for the shared skip path); this kernel
 // gathers the four taps of an output pixel from both, adds the bias, applies the sigmoid, accumulates the squared error
 // against the target frame and writes d(loss)/d(raw) -- one pass, no raw-output tensor, 32-bit index arithmetic.
-template <typename T>
+template <typename T, int C>
 __global__ void __launch_bounds__(256) convt_c1_loss_kernel(const T* __restrict__ col, const T* __restrict__ col2, const int* __restrict__ grp_src,
                                                             const float* __restrict__ bias, const float* __restrict__ x,
                                                             const int* __restrict__ tgt, const float* __restrict__ coef, int B, int Hi,
                                                             int Wi, T* __restrict__ d_raw, float* __restrict__ partial) {
   const int g = blockIdx.y;
   const unsigned Ho = 2u * Hi, Wo = 2u * Wi;
-  const unsigned E = (unsigned)B * Ho * Wo;
-  const float* xt = x + (long long)tgt[g] * E;
-  const T* cg = col + (long long)g * B * Hi * Wi * 16;
-  const T* sg = col2 + (long long)grp_src[g] * B * Hi * Wi * 16;
-  T* dg = d_raw + (long long)g * E;
-  const float cf = coef[g], b0 = bias ? bias[0] : 0.f;
+  const unsigned P = (unsigned)B * Ho * Wo;   // output pixels of the group; E = P * C elements
+  const float* xt = x + (long long)tgt[g] * P * C;
+  const T* cg = col + (long long)g * B * Hi * Wi * 16 * C;
+  const T* sg = col2 + (long long)grp_src[g] * B * Hi * Wi * 16 * C;
+  T* dg = d_raw + (long long)g * P * C;
+  const float cf = coef[g];
+  float b0[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) b0[c] = bias ? bias[c] : 0.f;
   double acc = 0.0;
-  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < P; e += gridDim.x * blockDim.x) {
     const unsigned ox = e % Wo, r = e / Wo, oy = r % Ho, b = r / Ho;
     const int kh0 = (oy + 1) & 1, kw0 = (ox + 1) & 1;
-    float v = b0;
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) v[c] = b0[c];
 #pragma unroll
     for (int a = 0; a < 2; a++) {
 #pragma unroll
-      for (int c = 0; c < 2; c++) {
-        const int kh = kh0 + 2 * a, kw = kw0 + 2 * c;
+      for (int q = 0; q < 2; q++) {
+        const int kh = kh0 + 2 * a, kw = kw0 + 2 * q;
         const int ty = (int)oy + 1 - kh, tx = (int)ox + 1 - kw;
         const int iy = ty >> 1, ix = tx >> 1;
         if (ty < 0 || iy >= Hi || tx < 0 || ix >= Wi) continue;
-        const unsigned off = (((b * Hi + iy) * Wi + ix) << 4) + kh * 4 + kw;
-        v += ld_f<T>(cg + off) + ld_f<T>(sg + off);
+        const unsigned off = ((((b * Hi + iy) * Wi + ix) << 4) + kh * 4 + kw) * C;
+#pragma unroll
+        for (int c = 0; c < C; c++) v[c] += ld_f<T>(cg + off + c) + ld_f<T>(sg + off + c);
       }
     }
-    const float s = sigmoidf_(v);
-    const float d = s - xt[e];
-    acc += (double)d * (double)d;
-    st_f<T>(dg + e, cf * 2.f * d * s * (1.f - s));
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const float s = sigmoidf_(v[c]);
+      const float d = s - xt[e * C + c];
+      acc += (double)d * (double)d;
+      st_f<T>(dg + e * C + c, cf * 2.f * d * s * (1.f - s));
+    }
   }
   __shared__ double sh[8];
   acc = warp_sum_d(acc);
@@ -151,12 +160,18 @@ int p2pvg_sigmoid_mse_impl(const void* raw, int dtype, const float* x, const int
 }
 
 int p2pvg_convt_c1_loss_impl(const void* col, const void* col2, int dtype, const int* grp_src, const float* bias, const float* x, const int* tgt,
-                             const float* coef, int G, int B, int Hi, int Wi, void* d_raw, float* partial, cudaStream_t st) {
+                             const float* coef, int G, int B, int Hi, int Wi, int C, void* d_raw, float* partial, cudaStream_t st) {
   if (G == 0 || B == 0) return P2PVG_OK;
-  P2PVG_REQUIRE((long long)B * Hi * Wi * 16 < (1LL << 31), P2PVG_ERR_UNSUPPORTED, "convt_c1_loss: group too large for 32-bit indexing");
+  P2PVG_REQUIRE(C == 1 || C == 3, P2PVG_ERR_UNSUPPORTED, "convt_c1_loss: 1 or 3 output channels (got %d)", C);
+  P2PVG_REQUIRE((long long)B * Hi * Wi * 16 * C < (1LL << 31), P2PVG_ERR_UNSUPPORTED, "convt_c1_loss: group too large for 32-bit indexing");
   dim3 grid(MSE_CHUNKS, G);
-  DISPATCH_DTYPE(dtype, T, (convt_c1_loss_kernel<T><<<grid, 256, 0, st>>>((const T*)col, (const T*)col2, grp_src, bias, x, tgt, coef, B, Hi, Wi,
-                                                                          (T*)d_raw, partial)));
+  if (C == 1) {
+    DISPATCH_DTYPE(dtype, T, (convt_c1_loss_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)col, (const T*)col2, grp_src, bias, x, tgt, coef, B, Hi, Wi,
+                                                                               (T*)d_raw, partial)));
+  } else {
+    DISPATCH_DTYPE(dtype, T, (convt_c1_loss_kernel<T, 3><<<grid, 256, 0, st>>>((const T*)col, (const T*)col2, grp_src, bias, x, tgt, coef, B, Hi, Wi,
+                                                                               (T*)d_raw, partial)));
+  }
   return p2pvg_check_launch("convt_c1_loss");
 }
 

@@ -803,8 +803,8 @@ class TrainEngine:
                 else:
                     K.gemm(d, wD, colD, Md, 16 * cout, cd, b_mn=True)
                     K.gemm(skip, wS, colS, Ms, 16 * cout, cd, b_mn=True)
-                if k == n - 1 and cout == 1 and self.fuse_last:
-                    # last layer of a 1-channel stack: the tap gather, sigmoid and loss run as ONE kernel in losses_fwd
+                if k == n - 1 and cout in (1, 3) and self.fuse_last:
+                    # last layer of a 1- / 3-channel stack: the tap gather, sigmoid and loss run as ONE kernel in losses_fwd
                     rec_fused = (colD, colS, Hi, P[cn + ".bias"])
                 else:
                     K.col2im(colD, raw, N, Hi, Hi, cout, bias=P[cn + ".bias"], col2=colS, grp_src=self.ix["skip_src"], imgs_per_group=B)
@@ -835,7 +835,7 @@ class TrainEngine:
         if fl is not None:
             colD, colS, Hi, bias = fl
             K.convt_c1_loss(colD, colS, self.ix["skip_src"], bias, self.x_nhwc, self.ix["tgt_idx"], self.coef, G, B, Hi, Hi,
-                            self.d_rawout, self.mse_partial)
+                            self.d_rawout, self.mse_partial, C=self.nc)
         else:
             K.sigmoid_mse(raw, self.x_nhwc, self.ix["tgt_idx"], self.coef, G, E, None, self.d_rawout, self.mse_partial)
         self.align_partial = self.fbuf("align_partial", max(S, 1))

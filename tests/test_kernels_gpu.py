@@ -341,37 +341,39 @@ def test_sigmoid_mse_finalize_adam(KS, dtype):
         close(a, b, rtol=1e-5, atol=1e-7)
 
 
-def test_convt_c1_loss_equals_col2im_plus_sigmoid_mse():
+@pytest.mark.parametrize("C", [1, 3])
+def test_convt_c1_loss_equals_col2im_plus_sigmoid_mse(C):
     """Fused last decoder layer (tap gather + bias + sigmoid + MSE + d raw) against the two-kernel path it replaces."""
     from p2pvg_b200._lib import CudaKernels
     K = CudaKernels("cuda")
     torch.manual_seed(0)
     G, B, Hi, nsrc, T = 5, 3, 8, 2, 7
     N = G * B
-    col = (torch.randn(N * Hi * Hi, 16, device="cuda") * 0.5).bfloat16()
-    col2 = (torch.randn(nsrc * B * Hi * Hi, 16, device="cuda") * 0.5).bfloat16()
+    col = (torch.randn(N * Hi * Hi, 16 * C, device="cuda") * 0.5).bfloat16()
+    col2 = (torch.randn(nsrc * B * Hi * Hi, 16 * C, device="cuda") * 0.5).bfloat16()
     src = torch.tensor([0, 1, 1, 0, 1], dtype=torch.int32, device="cuda")
     tgt = torch.tensor([1, 2, 3, 4, 6], dtype=torch.int32, device="cuda")
-    bias = torch.tensor([0.3], device="cuda")
-    E = B * 4 * Hi * Hi
+    bias = torch.tensor([0.3, -0.2, 0.1][:C], device="cuda")
+    E = B * 4 * Hi * Hi * C
     x = torch.rand(T, E, device="cuda")
     coef = torch.rand(G, device="cuda") + 0.5
-    raw = torch.empty(N * 4 * Hi * Hi, device="cuda", dtype=torch.bfloat16)
-    K.col2im(col, raw, N, Hi, Hi, 1, bias=bias, col2=col2, grp_src=src, imgs_per_group=B)
+    raw = torch.empty(N * 4 * Hi * Hi * C, device="cuda", dtype=torch.bfloat16)
+    K.col2im(col, raw, N, Hi, Hi, C, bias=bias, col2=col2, grp_src=src, imgs_per_group=B)
     d_ref = torch.empty_like(raw)
     p_ref = torch.zeros(G * K.mse_chunks(), device="cuda")
     K.sigmoid_mse(raw, x, tgt, coef, G, E, None, d_ref, p_ref)
     d_got = torch.empty_like(raw)
     p_got = torch.zeros(G * K.mse_chunks(), device="cuda")
-    K.convt_c1_loss(col, col2, src, bias, x, tgt, coef, G, B, Hi, Hi, d_got, p_got)
+    K.convt_c1_loss(col, col2, src, bias, x, tgt, coef, G, B, Hi, Hi, d_got, p_got, C=C)
     # the two-kernel path rounds the pre-sigmoid value to bf16 once more than the fused one
     assert torch.allclose(p_got.reshape(G, -1).sum(1), p_ref.reshape(G, -1).sum(1), rtol=5e-3)
     assert (d_got.float() - d_ref.float()).abs().max().item() <= 2e-2 * d_ref.float().abs().max().item()
-    # exact check against torch on the same bf16 operands
-    c = col.float().reshape(G, B, Hi, Hi, 4, 4)
-    c2 = col2.float().reshape(nsrc, B, Hi, Hi, 4, 4)[src.long()]
-    tot = (c + c2).permute(0, 1, 4, 5, 2, 3).reshape(N, 16, Hi * Hi)
-    want = torch.nn.functional.fold(tot, (2 * Hi, 2 * Hi), kernel_size=4, stride=2, padding=1).reshape(G, E) + 0.3
+    # exact check against torch on the same bf16 operands: col is [pixel][tap][channel]
+    c = col.float().reshape(G, B, Hi, Hi, 4, 4, C)
+    c2 = col2.float().reshape(nsrc, B, Hi, Hi, 4, 4, C)[src.long()]
+    tot = (c + c2).permute(0, 1, 6, 4, 5, 2, 3).reshape(N, C * 16, Hi * Hi)   # fold wants [N, C*kh*kw, L]
+    want = torch.nn.functional.fold(tot, (2 * Hi, 2 * Hi), kernel_size=4, stride=2, padding=1)   # [N, C, 2Hi, 2Hi]
+    want = (want + bias.view(1, C, 1, 1)).permute(0, 2, 3, 1).reshape(G, E)                      # NHWC per group
     s = torch.sigmoid(want)
     diff = s - x[tgt.long()]
     assert torch.allclose(p_got.reshape(G, -1).sum(1), (diff * diff).sum(1), rtol=1e-4)
