@@ -46,6 +46,9 @@ struct Geom {
   int bw64;
   int imgs_per_group;   // addend indexing
   int add_bf16;         // the addend tensor is bf16 (half the epilogue read traffic of the fp32 form)
+  int bres;             // kind 0, BN = 64, one channel chunk, <= 9 taps: ALL weight tiles stay resident in shared memory for the whole
+                        // kernel (72 KB) and only the A boxes stream through a 7-slot ring -- the 64 -> 64 channel 3x3 layers re-fetched
+                        // their 73 KB of weights for every 128-pixel tile (43 FLOP per filled byte -> 65)
   int swap;             // kind 1 with the operand roles swapped: M = taps*Cn (gathered map), N = Cm (few output channels would waste
                         // half of a 128-row MMA tile otherwise); the partial sums are [taps*Cn][Cm] and the reduce kernel transposes
   int ks, st, sgn;      // filter taps per side (4 | 3), stride between the two maps (2 | 1), tap-offset sign (+1 | -1)
@@ -114,7 +117,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + C_::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C_::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* bres_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  // resident-weight mode (kind 0, BN = 64): weights at [0, 9 * 8 KB), A ring of 7 x 16 KB behind them
+  const bool bres = (KIND == 0) && (BN == 64) && g.bres != 0;
+  constexpr int BRES_B_BYTES = 9 * 64 * 128, BRES_STAGES = 7;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (g.Ntot + BN - 1) / BN;
@@ -134,6 +141,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 4);
     }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -150,6 +158,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
+      if (bres) {   // all weight taps once: [tap][64 output channels][64 input channels]
+        mbar_expect_tx(bres_bar, (uint32_t)(g.ks * g.ks) * 64 * 128);
+        for (int tap = 0; tap < g.ks * g.ks; tap++) tma_load_2d(&tmB, bres_bar, smem + tap * 64 * 128, tap * 64, 0);
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         // tile decode with as few integer divisions as possible: the producer thread is the latency-critical one
         // kind 2: the output-parity phase is the FASTEST tile index, so that the four phases of one pixel tile run on four
@@ -203,16 +215,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         for (int kb = kb0; kb < kb1; kb++, it++) {
-          const int s = it % C_::STAGES;
-          const uint32_t par = (it / C_::STAGES) & 1;
+          // (both divisors are compile-time constants: no runtime division in the single producer / issuer threads)
+          const int s = bres ? (int)(it % BRES_STAGES) : (int)(it % C_::STAGES);
+          const uint32_t par = (bres ? (it / BRES_STAGES) : (it / C_::STAGES)) & 1;
           mbar_wait(&empty_bar[s], par ^ 1);
-          uint8_t* sa = smem + s * C_::STAGE_BYTES;
+          uint8_t* sa = bres ? smem + BRES_B_BYTES + s * A_STAGE_BYTES : smem + s * C_::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[s], bres ? A_STAGE_BYTES : C_::STAGE_BYTES);
           if (KIND == 0) {
             // (kh, kw, channel chunk) advance incrementally (kinds 0 / 2 never split K: kb starts at 0)
             tma_load_4d(&tmA, &full_bar[s], sa, t_cc * 64, g.sgn * (t_kw - 1), g.st * py0 + g.sgn * (t_kh - 1), pn0);
-            tma_load_2d(&tmB, &full_bar[s], sb, kb * 64, n0);   // (tap * Ck + c0) == kb * 64
+            if (!bres) tma_load_2d(&tmB, &full_bar[s], sb, kb * 64, n0);   // (tap * Ck + c0) == kb * 64
             if (++t_cc == cchunks) { t_cc = 0; if (++t_kw == g.ks) { t_kw = 0; t_kh++; } }
           } else if (KIND == 2) {
             const int tq = t_kh, c0 = t_cc * 64;   // t_kh doubles as the 2x2 tap index of this phase
@@ -262,6 +275,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint64_t da0 = A_MN ? make_desc(smem0, 64 * 128, 1024) : make_desc(smem0, 0, 1024);
       const uint64_t db0 = B_MN ? make_desc(smem0 + A_STAGE_BYTES, 64 * 128, 1024) : make_desc(smem0 + A_STAGE_BYTES, 0, 1024);
       uint32_t it = 0, lt = 0;
+      if (bres) {
+        mbar_wait(bres_bar, 0);   // the resident weights have landed
+        tcgen05_fence_after();
+      }
+      const uint64_t da0r = make_desc(smem0 + BRES_B_BYTES, 0, 1024), db0r = make_desc(smem0, 0, 1024);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, lt++) {
         int z = 0;
         if (splits > 1) z = t / tiles_mn;   // only kind 1 splits K (one phase)
@@ -271,17 +289,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tcgen05_fence_after();
         const uint32_t tmem_c = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; kb++, it++) {
-          const int s = it % C_::STAGES;
-          const uint32_t par = (it / C_::STAGES) & 1;
+          // (both divisors are compile-time constants: no runtime division in the single producer / issuer threads)
+          const int s = bres ? (int)(it % BRES_STAGES) : (int)(it % C_::STAGES);
+          const uint32_t par = (bres ? (it / BRES_STAGES) : (it / C_::STAGES)) & 1;
           mbar_wait(&full_bar[s], par);
           tcgen05_fence_after();
           // descriptors of stage 0 / k 0 are built once; the start-address field (bits 0-13, address >> 4) is advanced by
           // plain additions -- the single issuing thread has ~32 clk per 128x64x16 MMA to spend
           const uint64_t stage_off = (uint64_t)((uint32_t)s * (uint32_t)(C_::STAGE_BYTES >> 4));
+          const uint64_t a_off = bres ? (uint64_t)((uint32_t)s * (uint32_t)(A_STAGE_BYTES >> 4)) : stage_off;
+          const uint64_t b_off = bres ? (uint64_t)((uint32_t)kb * (uint32_t)((64 * 128) >> 4)) : stage_off;   // resident: tap kb
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; k++) {
-            const uint64_t da = da0 + stage_off + (uint64_t)(k * ((A_MN ? UMMA_K * 128 : 32) >> 4));
-            const uint64_t db = db0 + stage_off + (uint64_t)(k * ((B_MN ? UMMA_K * 128 : 32) >> 4));
+            const uint64_t da = (bres ? da0r : da0) + a_off + (uint64_t)(k * ((A_MN ? UMMA_K * 128 : 32) >> 4));
+            const uint64_t db = (bres ? db0r : db0) + b_off + (uint64_t)(k * ((B_MN ? UMMA_K * 128 : 32) >> 4));
             umma_bf16(tmem_c, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
@@ -747,6 +768,7 @@ int g_convt4_max_cn = 64;   // kind 2 with at most this many output channels: th
                             // 0 = off).  Measured (C2 step, B200): 64 -> -0.36 ms; 128 -> +0.1 ms (the N = 64 MMAs of the fused tile issue twice as
                             // many instructions as the 128-wide phase tiles, which outweighs the saved operand fills)
 int g_convt4_attr[2] = {};
+int g_bres = 1;      // 64 -> 64 channel 3x3 layers: weights resident in shared memory (P2PVG_CONV_BRES=0 disables)
 int g_k1_swap = 1;   // kind 1 / 4 with 64 output channels: swapped operand roles (P2PVG_K1_SWAP=0 disables)
 
 void resolve2() {
@@ -759,6 +781,8 @@ void resolve2() {
   (void)cudaGetLastError();
   const char* e = getenv("P2PVG_CONV_BN256");
   if (e != nullptr && e[0] == '0') g_bn256 = 0;
+  const char* br = getenv("P2PVG_CONV_BRES");
+  if (br != nullptr && br[0] == '0') g_bres = 0;
   const char* sw = getenv("P2PVG_K1_SWAP");
   if (sw != nullptr && sw[0] == '0') g_k1_swap = 0;
   const char* f4 = getenv("P2PVG_CONVT4_MAX_CN");
@@ -882,6 +906,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
   g.N = N; g.H = H; g.W = W; g.Ck = Ck; g.Cn = Cn; g.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : 1;
   g.add_bf16 = (addend != nullptr && addend_dtype == P2PVG_BF16) ? 1 : 0;
   g.swap = 0;
+  g.bres = 0;
   g.ks = kind >= 3 ? 3 : 4; g.st = kind >= 3 ? 1 : 2; g.sgn = kind == 5 ? -1 : 1;
   const int taps = g.ks * g.ks;
   if (kind == 3 || kind == 5) kind = 0;
@@ -915,6 +940,7 @@ int p2pvg_conv_gemm_impl(int kind, const void* a, const void* b, long long ldb, 
     rc = map2d(&tb, b, (long long)taps * Ck, Cn, ldb, BN);
     if (rc) return rc;
     const int nkb = taps * (Ck / 64);
+    g.bres = (BN == 64 && Cn == 64 && Ck == 64 && taps <= 9 && g_bres) ? 1 : 0;
     if (BN == 256) return launch<0, 256>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
     if (BN == 128) return launch<0, 128>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
     return launch<0, 64>(ta, tb, c, c_dtype, ldc, g, accumulate, bias, addend, grp_src, nullptr, 1, nkb, st, stat_partial);
