@@ -207,6 +207,8 @@ int p2pvg_lstm_scan_bwd(const float* dhtop, const float* whh, const float* gates
 /* diagnostics: cudaOccupancyMaxActiveClusters of the hidden-size-512 scans (clusters of 16 CTAs): which = 0 forward (16-row
  * slabs), 1 forward (32-row slabs), 2 backward; -1 on error */
 int p2pvg_lstm_cluster512_max_clusters(int which);
+/* the same for the hidden-size-256 scans (clusters of 8 CTAs): which = 0 / 1 forward with 16- / 32-row slabs, 2 / 3 backward */
+int p2pvg_lstm_cluster_max_clusters(int which);
 /* gaussian_lstm.reparameterize (models/lstm.py:76-81) for posterior and prior + KLCriterion.forward
  * (misc/criterion.py:10-15) summed over all elements (division by opt.batch_size happens in finalize_losses). */
 int p2pvg_reparam_kl_fwd(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,

@@ -83,6 +83,7 @@ int p2pvg_lstm_scan_bwd_impl(const float*, const float*, const float*, const flo
 int p2pvg_lstm_cluster512_fwd_impl(const float*, const float*, const float*, float*, float*, float*, int, int, cudaStream_t);
 int p2pvg_lstm_cluster512_bwd_impl(const float*, const float*, const float*, const float*, float*, int, int, cudaStream_t);
 int p2pvg_lstm_cluster512_max_clusters_impl(int);
+int p2pvg_lstm_cluster_max_clusters_impl(int);
 int p2pvg_reparam_kl_fwd_impl(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, int,
                               float*, cudaStream_t);
 int p2pvg_reparam_kl_bwd_impl(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
@@ -279,6 +280,7 @@ int p2pvg_lstm_scan_bwd(const float* dhtop, const float* whh, const float* gates
   return p2pvg_lstm_scan_bwd_impl(dhtop, whh, gates, cs, dG, S, B, R, tf32, counter, ST);
 }
 int p2pvg_lstm_cluster512_max_clusters(int which) { return p2pvg_lstm_cluster512_max_clusters_impl(which); }
+int p2pvg_lstm_cluster_max_clusters(int which) { return p2pvg_lstm_cluster_max_clusters_impl(which); }
 int p2pvg_reparam_kl_fwd(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,
                          const float* eps_p, float* z, float* z_p, int n, float* kl_sum, void* stream) {
   return p2pvg_reparam_kl_fwd_impl(mu, lv, mu_p, lv_p, eps, eps_p, z, z_p, n, kl_sum, ST);

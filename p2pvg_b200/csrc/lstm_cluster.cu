@@ -365,6 +365,34 @@ int launch_bwd(const float* dhtop, const float* whh, const float* gates, const f
 
 bool p2pvg_lstm_cluster_supported(int R) { return R == 64 || R == 128 || R == 256; }
 
+// diagnostics: cudaOccupancyMaxActiveClusters of the R = 256 scans (clusters of 8): which = 0 fwd MT=1, 1 fwd MT=2, 2 bwd MT=1, 3 bwd MT=2
+int p2pvg_lstm_cluster_max_clusters_impl(int which) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS * 64);
+  cfg.blockDim = dim3(NT);
+  int n = -1;
+  cudaError_t e;
+  if (which == 0) {
+    cfg.dynamicSmemBytes = fwd_smem<256, 1>();
+    cudaFuncSetAttribute(lstm_cl_fwd_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<256, 1>());
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl_fwd_kernel<256, 1>, &cfg);
+  } else if (which == 1) {
+    cfg.dynamicSmemBytes = fwd_smem<256, 2>();
+    cudaFuncSetAttribute(lstm_cl_fwd_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<256, 2>());
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl_fwd_kernel<256, 2>, &cfg);
+  } else if (which == 2) {
+    cfg.dynamicSmemBytes = bwd_smem<256, 1>();
+    cudaFuncSetAttribute(lstm_cl_bwd_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<256, 1>());
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl_bwd_kernel<256, 1>, &cfg);
+  } else {
+    cfg.dynamicSmemBytes = bwd_smem<256, 2>();
+    cudaFuncSetAttribute(lstm_cl_bwd_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<256, 2>());
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl_bwd_kernel<256, 2>, &cfg);
+  }
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  return n;
+}
+
 // rows per slab: 32 (MT = 2) above this batch size.  P2PVG_LSTM_MT2_ABOVE overrides (experiments).
 static int mt2_above() {
   static const int v = [] { const char* e = getenv("P2PVG_LSTM_MT2_ABOVE"); return e ? atoi(e) : 128; }();

@@ -11,6 +11,8 @@ from p2pvg_b200._lib import CudaKernels  # noqa: E402
 K = CudaKernels("cuda")
 print("cluster-16 scans: cudaOccupancyMaxActiveClusters fwd(16 rows) / fwd(32 rows) / bwd =",
       [K.lib.p2pvg_lstm_cluster512_max_clusters(i) for i in range(3)])
+print("cluster-8 scans (R=256): max active clusters fwd MT1 / fwd MT2 / bwd MT1 / bwd MT2 =",
+      [K.lib.p2pvg_lstm_cluster_max_clusters(i) for i in range(4)])
 S, R = 30, int(os.environ.get("R", "256"))
 for B in (16, 64, 128, 256):
     dev = "cuda"
