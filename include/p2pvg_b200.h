@@ -149,6 +149,11 @@ int p2pvg_col2im_k4s2p1(const void* col, const void* col2, const int* grp_src, i
 /* dst (contiguous, dims[4]) = src gathered with per-destination-dimension strides (weight packing, NCHW->NHWC, casts). */
 int p2pvg_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims /*host*/,
                    const int64_t* src_strides /*host*/, int accumulate, void* stream);
+/* Frames x [N, C, H*W] fp32 (the layout data/*.py hands to P2PModel.forward, models/p2p_model.py:185-197) -> channels-last
+ * [N, H*W, C], written once in fp32 (dst_f32: the MSE target, may be NULL) and once in the activation dtype (dst_act: input
+ * of the first convolution, may be NULL) from a single read.  C in {2,3,4}, H*W % 4 == 0; one-channel frames need no
+ * conversion (NCHW == NHWC). */
+int p2pvg_nchw_to_nhwc_dual(const float* src, float* dst_f32, void* dst_act, int act_dtype, int64_t N, int hw, int C, void* stream);
 int p2pvg_add_indexed(void* dst, const void* src, int dtype, const int* dst_idx, int F, int64_t n, void* stream);
 int p2pvg_group_sum(const void* in, void* out, int dtype, const int* grp_src, int G, int F, int64_t n, void* stream);
 /* dst[a][q][p] = src[a][p][q] for a < A (tiled, coalesced both ways): nn.Conv2d / nn.ConvTranspose2d weights

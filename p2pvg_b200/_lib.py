@@ -226,6 +226,12 @@ class CudaKernels:
         s = (_i64 * 4)(*strides)
         self._ck(self.lib.p2pvg_permute4(_p(src), _i(_dt(src)), _p(dst), _i(_dt(dst)), d, s, _i(int(accumulate)), self._stream()))
 
+    def nchw_to_nhwc_dual(self, src, dst_f32, dst_act, N, hw, C):
+        """frames [N,C,hw] fp32 -> [N,hw,C] in fp32 and/or the activation dtype from one read"""
+        self._ck(self.lib.p2pvg_nchw_to_nhwc_dual(_p(src), _p(dst_f32) if dst_f32 is not None else None,
+                                                  _p(dst_act) if dst_act is not None else None,
+                                                  _i(_dt(dst_act) if dst_act is not None else 0), _i64(N), _i(hw), _i(C), self._stream()))
+
     def add_indexed(self, dst, src, dst_idx, F, n):
         self._ck(self.lib.p2pvg_add_indexed(_p(dst), _p(src), _i(_dt(dst)), _p(dst_idx), _i(F), _i64(n), self._stream()))
 

@@ -59,6 +59,7 @@ int p2pvg_upsample2_bwd_impl(const void*, void*, int, int, int, int, int, cudaSt
 int p2pvg_gather_add_impl(void*, int, const float*, const int*, int, long long, cudaStream_t);
 int p2pvg_col2im_k4s2p1_impl(const void*, const void*, const int*, int, void*, int, int, int, int, int, const float*, int, cudaStream_t);
 int p2pvg_permute4_impl(const void*, int, void*, int, const int*, const long long*, int, cudaStream_t);
+int p2pvg_nchw_to_nhwc_dual_impl(const float*, float*, void*, int, long long, int, int, cudaStream_t);
 int p2pvg_add_indexed_impl(void*, const void*, int, const int*, int, long long, cudaStream_t);
 int p2pvg_group_sum_impl(const void*, void*, int, const int*, int, int, long long, cudaStream_t);
 int p2pvg_blockdiag_impl(const void*, int, void*, int, int, int, int, cudaStream_t);
@@ -177,6 +178,9 @@ int p2pvg_col2im_k4s2p1(const void* col, const void* col2, const int* grp_src, i
 int p2pvg_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims, const int64_t* src_strides,
                    int accumulate, void* stream) {
   return p2pvg_permute4_impl(src, src_dtype, dst, dst_dtype, dims, (const long long*)src_strides, accumulate, ST);
+}
+int p2pvg_nchw_to_nhwc_dual(const float* src, float* dst_f32, void* dst_act, int act_dtype, int64_t N, int hw, int C, void* stream) {
+  return p2pvg_nchw_to_nhwc_dual_impl(src, dst_f32, dst_act, act_dtype, (long long)N, hw, C, ST);
 }
 int p2pvg_add_indexed(void* dst, const void* src, int dtype, const int* dst_idx, int F, int64_t n, void* stream) {
   return p2pvg_add_indexed_impl(dst, src, dtype, dst_idx, F, n, ST);

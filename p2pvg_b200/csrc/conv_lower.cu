@@ -197,6 +197,52 @@ __global__ void permute4_kernel(const TS* __restrict__ src, TD* __restrict__ dst
   }
 }
 
+// ---- frames NCHW fp32 -> NHWC, both precisions from one read: the fp32 copy is the MSE target, the activation-dtype copy
+// feeds the first convolution.  One thread = 4 consecutive pixels of one frame: C float4 plane loads (coalesced per
+// plane), 4*C contiguous outputs.
+template <int C, typename TA>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_dual_kernel(const float* __restrict__ src, float* __restrict__ dst32,
+                                                                TA* __restrict__ dsta, long long N, int hw4) {
+  const long long total = N * hw4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / hw4;
+    const int p4 = (int)(idx - n * hw4);
+    const float* s = src + (n * C * hw4 + p4) * 4;
+    float v[C][4];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const float4 t = *reinterpret_cast<const float4*>(s + (long long)c * hw4 * 4);
+      v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w;
+    }
+    float o[4 * C];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int c = 0; c < C; c++) o[q * C + c] = v[c][q];
+    const long long ob = idx * 4 * C;
+    if (dst32) {
+#pragma unroll
+      for (int j = 0; j < C; j++) *reinterpret_cast<float4*>(dst32 + ob + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+    if (dsta) {
+      if constexpr (sizeof(TA) == 2) {   // 4*C bf16 = C 8-byte stores
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(o[4 * j], o[4 * j + 1]), hi = __floats2bfloat162_rn(o[4 * j + 2], o[4 * j + 3]);
+          uint2 u;
+          u.x = *reinterpret_cast<const unsigned*>(&lo);
+          u.y = *reinterpret_cast<const unsigned*>(&hi);
+          *reinterpret_cast<uint2*>(dsta + ob + 4 * j) = u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < C; j++)
+          *reinterpret_cast<float4*>(dsta + ob + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+    }
+  }
+}
+
 // ---- dst[dst_idx[f]] += src[f] over F groups of n elements -------------------------------------
 template <typename T>
 __global__ void add_indexed_kernel(T* __restrict__ dst, const T* __restrict__ src, const int* __restrict__ dst_idx, int F, long long n) {
@@ -342,6 +388,27 @@ int p2pvg_permute4_impl(const void* src, int src_dtype, void* dst, int dst_dtype
   }
 #undef L
   return p2pvg_check_launch("permute4");
+}
+
+int p2pvg_nchw_to_nhwc_dual_impl(const float* src, float* dst32, void* dsta, int act_dtype, long long N, int hw, int C, cudaStream_t st) {
+  if (N == 0) return P2PVG_OK;
+  if (hw % 4 != 0 || (C != 2 && C != 3 && C != 4) || (!dst32 && !dsta)) {
+    p2pvg_set_error("nchw_to_nhwc_dual: needs H*W % 4 == 0, C in {2,3,4} and at least one destination");
+    return P2PVG_ERR_UNSUPPORTED;
+  }
+  const int hw4 = hw / 4;
+  const int g = grid_for(N * hw4, 256);
+#define L(CC, TA) nchw_to_nhwc_dual_kernel<CC, TA><<<g, 256, 0, st>>>(src, dst32, (TA*)dsta, N, hw4)
+#define LC(TA) do { if (C == 2) L(2, TA); else if (C == 3) L(3, TA); else L(4, TA); } while (0)
+  if (!dsta || act_dtype == P2PVG_F32) LC(float);
+  else if (act_dtype == P2PVG_BF16) LC(bf16);
+  else {
+    p2pvg_set_error("nchw_to_nhwc_dual: bad activation dtype");
+    return P2PVG_ERR_BAD_ARG;
+  }
+#undef LC
+#undef L
+  return p2pvg_check_launch("nchw_to_nhwc_dual");
 }
 
 int p2pvg_add_indexed_impl(void* dst, const void* src, int dtype, const int* dst_idx, int F, long long n, cudaStream_t st) {

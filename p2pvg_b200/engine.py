@@ -565,14 +565,22 @@ class TrainEngine:
         xs = x.contiguous()
         if nc == 1 and xs.dtype == torch.float32:
             self.x_nhwc = xs.view(-1)  # one channel: NCHW == NHWC, the MSE target is the input itself
+            dual = False
         else:
             self.x_nhwc = self.fbuf("x_nhwc", N * hw * nc)
-            K.permute4(xs, self.x_nhwc, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
+            dual = xs.dtype == torch.float32 and nc in (2, 3, 4) and hw % 4 == 0 and xs.is_cuda
+            if not dual:
+                K.permute4(xs, self.x_nhwc, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
         if self.adt == torch.float32:
             a = self.x_nhwc
+            if dual:
+                K.nchw_to_nhwc_dual(xs, self.x_nhwc, None, N, hw, nc)
         else:
             a = self.buf("x_act", N * hw * nc)
-            K.permute4(xs, a, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
+            if dual:  # one read of the frames, both copies
+                K.nchw_to_nhwc_dual(xs, self.x_nhwc, a, N, hw, nc)
+            else:
+                K.permute4(xs, a, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
         self.enc_in = a
         self.enc = []
         H = W0

@@ -167,6 +167,28 @@ def test_permute4(KS, sd, dd):
     assert torch.equal(d2.float().reshape(6, 4, 4, 5)[:, 1, 2, 3], (2 * w.float()[:, 3, 1, 2]).to(dd).float())
 
 
+@pytest.mark.parametrize("C", [2, 3, 4])
+@pytest.mark.parametrize("adt", [torch.bfloat16, torch.float32, None])
+def test_nchw_to_nhwc_dual(KS, C, adt):
+    """frames NCHW -> channels-last in fp32 and the activation dtype from one read: a pure data movement, bit exact against
+    torch.permute (+ round-to-nearest bf16 cast)"""
+    Kc, _ = KS
+    N, H = 37, 12
+    x = rnd(N, C, H, H, seed=40 + C)
+    d32 = torch.zeros(N * H * H * C, device="cuda")
+    da = torch.zeros(N * H * H * C, device="cuda", dtype=adt) if adt is not None else None
+    Kc.nchw_to_nhwc_dual(x, d32, da, N, H * H, C)
+    want = x.permute(0, 2, 3, 1).contiguous().view(-1)
+    assert torch.equal(d32, want)
+    if da is not None:
+        assert torch.equal(da, want.to(adt))
+        d32b = torch.zeros_like(d32)
+        Kc.nchw_to_nhwc_dual(x, None, da.zero_(), N, H * H, C)      # activation copy only
+        assert torch.equal(da, want.to(adt)) and not d32b.any()
+    with pytest.raises(RuntimeError):
+        Kc.nchw_to_nhwc_dual(x, d32, da, N, H * H - 2, C)           # H*W % 4 != 0 is an error, not a fallback
+
+
 @pytest.mark.parametrize("dtype", DT)
 def test_add_indexed_group_sum(KS, dtype):
     Kc, Ke = KS
