@@ -401,7 +401,17 @@ def main():
     ms3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+    # host cost of enqueueing one step (no synchronisation inside the loop): what the GPU waits for after every
+    # synchronous loss read-back
+    torch.cuda.synchronize(dev)
+    th0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.step(x_dev, use_graph=use_graph, return_device=True)
+    host_enqueue_ms = (time.perf_counter() - th0) / args.steps * 1e3
+    torch.cuda.synchronize(dev)
+    barrier()
     e2e_detail = dict(ms_per_step=ms2.item() / args.steps, ms_per_step_batch_resident=ms3.item() / args.steps,
+                      host_enqueue_ms_per_step=host_enqueue_ms,
                       note="ms_per_step_batch_resident - device-timed ms_per_step = per-step host + sync latency; "
                            "ms_per_step - ms_per_step_batch_resident = exposed part of the H2D copy")
 

@@ -16,6 +16,7 @@
 // TF32 mma.sync m16n8k8 with fp32 accumulation, MUFU activations (error <= 2^-11, below the TF32 operand rounding) exactly
 // as in lstm_cluster.cu.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -75,10 +76,22 @@ lstm_cl16_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
   constexpr int KR = 16, KSM = KS - KR;    // register / shared-memory resident steps
   constexpr int CPT = (MB * UBc + NT - 1) / NT;
   constexpr int GL = NC + 1;
+  // 48-row slabs (MT = 3): the h slab alone takes what is left beside the weight half, so the partial gate sums are written
+  // over the part of the slab that has already been consumed (rows 0..31 -> slab rows 0..15, rows 32..47 -> slab rows 16..23),
+  // and the m16 tiles go through the tensor cores in two passes (2 + 1) to keep the accumulators at 32 registers.
+  constexpr bool ALIAS = MT > 2;
+  static_assert(MT <= 3, "slab rows");
+  static_assert(!ALIAS || (2 * 32 * GL == 16 * LD && 2 * 16 * GL == 8 * LD), "aliased partial-sum regions");
   extern __shared__ __align__(16) float sm[];
   float* Wsm = sm;                                   // [8 warps][KSM][TPW][2][32 lanes]
   float* Hb = Wsm + 8 * KSM * TPW * 2 * 32;          // [MB][LD]   h_{s-1} of the slab, TF32-rounded
-  float* Gs = Hb + MB * LD;                          // [2][MB][GL] partial gate pre-activations of the two K halves
+  float* Gs = ALIAS ? Hb : Hb + MB * LD;             // [2][rows][GL] partial gate pre-activations of the two K halves
+  float* bsm = ALIAS ? Hb + MB * LD : Gs + 2 * MB * GL;   // [4][UBc] b_hh of my units
+  // line of slab row `row`, K half h, in the partial-sum buffer
+  auto gs_line = [&](int row, int h) -> float* {
+    if constexpr (ALIAS) return row < 32 ? Gs + (h * 32 + row) * GL : Gs + 16 * LD + (h * 16 + row - 32) * GL;
+    else return Gs + (h * MB + row) * GL;
+  };
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_rank();
   const int r0 = (blockIdx.x / CS) * MB, u0 = (int)rank * UBc;
@@ -105,7 +118,7 @@ lstm_cl16_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
   // pointwise cells of this thread: (row, unit) = (ci / UBc, ci % UBc), ci = tid + NT*h
   int crow[CPT], cuu[CPT];
   bool cok[CPT];
-  float c_reg[CPT], bh[CPT][4];
+  float c_reg[CPT];
 #pragma unroll
   for (int h = 0; h < CPT; h++) {
     const int ci = tid + NT * h;
@@ -113,10 +126,9 @@ lstm_cl16_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
     cuu[h] = ci - crow[h] * UBc;
     cok[h] = ci < MB * UBc && (r0 + crow[h]) < B;
     c_reg[h] = cok[h] ? cs[(long long)(r0 + crow[h]) * R + u0 + cuu[h]] : 0.f;  // cs[0]
-#pragma unroll
-    for (int g = 0; g < 4; g++) bh[h][g] = cok[h] ? bhh[g * R + u0 + cuu[h]] : 0.f;
   }
-  __syncthreads();   // Wsm complete
+  if (tid < 4 * UBc) bsm[tid] = bhh[(tid / UBc) * R + u0 + tid % UBc];
+  __syncthreads();   // Wsm, bsm complete
 
   for (int s = 0; s < S; s++) {
     // input-side pre-activations of this step: independent of h, requested (not consumed) before the barrier
@@ -137,28 +149,31 @@ lstm_cl16_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
       *reinterpret_cast<float4*>(Hb + row * LD + k4 * 4) = v;
     }
     __syncthreads();
-    {
-      float acc[MT][TPW][4];
+    const float* ha = Hb + gq * LD + kh * (R / 2) + tq;
+    const float* wsm = Wsm + (warp * KSM * TPW * 2) * 32 + lane;
+    // MC m16 tiles starting at slab row m0: acc = h[m0 .. m0+16 MC) . W_hh^T over this warp's K half and 4 n8 tiles
+    auto gate_pass = [&](auto mc_tag, int m0) {
+      constexpr int MC = decltype(mc_tag)::value;
+      float acc[MC][TPW][4];
 #pragma unroll
-      for (int m = 0; m < MT; m++)
+      for (int m = 0; m < MC; m++)
 #pragma unroll
         for (int t = 0; t < TPW; t++)
 #pragma unroll
           for (int q = 0; q < 4; q++) acc[m][t][q] = 0.f;
-      const float* ha = Hb + gq * LD + kh * (R / 2) + tq;
+      const float* hp = ha + m0 * LD;
 #pragma unroll
       for (int k = 0; k < KR; k++) {
 #pragma unroll
-        for (int m = 0; m < MT; m++) {
+        for (int m = 0; m < MC; m++) {
           uint32_t a[4];
-          const float* hm = ha + m * 16 * LD + k * 8;
+          const float* hm = hp + m * 16 * LD + k * 8;
           a[0] = __float_as_uint(hm[0]); a[1] = __float_as_uint(hm[8 * LD]);
           a[2] = __float_as_uint(hm[4]); a[3] = __float_as_uint(hm[8 * LD + 4]);
 #pragma unroll
           for (int t = 0; t < TPW; t++) mma_tf32(acc[m][t], a, wreg[t][k]);
         }
       }
-      const float* wsm = Wsm + (warp * KSM * TPW * 2) * 32 + lane;
 #pragma unroll 4
       for (int k = 0; k < KSM; k++) {
         uint32_t b[TPW][2];
@@ -168,27 +183,33 @@ lstm_cl16_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
           b[t][1] = __float_as_uint(wsm[((k * TPW + t) * 2 + 1) * 32]);
         }
 #pragma unroll
-        for (int m = 0; m < MT; m++) {
+        for (int m = 0; m < MC; m++) {
           uint32_t a[4];
-          const float* hm = ha + m * 16 * LD + (KR + k) * 8;
+          const float* hm = hp + m * 16 * LD + (KR + k) * 8;
           a[0] = __float_as_uint(hm[0]); a[1] = __float_as_uint(hm[8 * LD]);
           a[2] = __float_as_uint(hm[4]); a[3] = __float_as_uint(hm[8 * LD + 4]);
 #pragma unroll
           for (int t = 0; t < TPW; t++) mma_tf32(acc[m][t], a, b[t]);
         }
       }
-      float* o = Gs + kh * MB * GL;
+      if constexpr (ALIAS) {
+        if (m0 == 0) __syncthreads();   // every warp is done with slab rows 0..31: their space now takes the partial sums
+      }
 #pragma unroll
-      for (int m = 0; m < MT; m++)
+      for (int m = 0; m < MC; m++)
 #pragma unroll
         for (int t = 0; t < TPW; t++) {
-          float* p = o + (m * 16 + gq) * GL + (ng * TPW + t) * 8 + 2 * tq;
+          float* p = gs_line(m0 + m * 16 + gq, kh) + (ng * TPW + t) * 8 + 2 * tq;
+          float* p8 = gs_line(m0 + m * 16 + gq + 8, kh) + (ng * TPW + t) * 8 + 2 * tq;
           p[0] = acc[m][t][0];
           p[1] = acc[m][t][1];
-          p[8 * GL] = acc[m][t][2];
-          p[8 * GL + 1] = acc[m][t][3];
+          p8[0] = acc[m][t][2];
+          p8[1] = acc[m][t][3];
         }
-    }
+    };
+    if constexpr (MT == 1) gate_pass(std::integral_constant<int, 1>{}, 0);
+    else gate_pass(std::integral_constant<int, 2>{}, 0);
+    if constexpr (MT == 3) gate_pass(std::integral_constant<int, 1>{}, 32);
     __syncthreads();
     float outv[CPT][5];
 #pragma unroll
@@ -197,7 +218,7 @@ lstm_cl16_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ wh
       const int row = crow[h], uu = cuu[h];
       float z[4];
 #pragma unroll
-      for (int g = 0; g < 4; g++) z[g] = (Gs[row * GL + g * UBc + uu] + Gs[MB * GL + row * GL + g * UBc + uu]) + (zp[h][g] + bh[h][g]);
+      for (int g = 0; g < 4; g++) z[g] = (gs_line(row, 0)[g * UBc + uu] + gs_line(row, 1)[g * UBc + uu]) + (zp[h][g] + bsm[g * UBc + uu]);
       const float ig = fast_sigmoid(z[0]), fg = fast_sigmoid(z[1]), gg = fast_tanh(z[2]), og = fast_sigmoid(z[3]);
       const float c = fg * c_reg[h] + ig * gg;
       c_reg[h] = c;
@@ -376,8 +397,9 @@ lstm_cl16_bwd_kernel(const float* __restrict__ dhtop, const float* __restrict__ 
 }
 
 constexpr size_t fwd_smem(int MT) {
-  return (size_t)(8 * 16 * 4 * 2 * 32 + 16 * MT * (R + PAD) + 2 * 16 * MT * (4 * UBc + 1)) * sizeof(float);
+  return (size_t)(8 * 16 * 4 * 2 * 32 + 16 * MT * (R + PAD) + (MT > 2 ? 0 : 2 * 16 * MT * (4 * UBc + 1)) + 4 * UBc) * sizeof(float);
 }
+static_assert(fwd_smem(3) <= 232448 && fwd_smem(2) <= 232448, "forward scan shared memory");
 constexpr size_t bwd_smem() { return (size_t)(8 * 8 * 8 * 2 * 32 + 2 * CS * 16 * UBc + 16 * (4 * UBc + PAD)) * sizeof(float); }
 
 template <typename Kern, typename... Args>
@@ -411,7 +433,7 @@ int launch_cluster16(Kern kern, const char* what, int grid, size_t smem, cudaStr
 
 }  // namespace
 
-// cudaOccupancyMaxActiveClusters of the cluster-16 scans (which = 0: forward MT=1, 1: forward MT=2, 2: backward); diagnostics
+// cudaOccupancyMaxActiveClusters of the cluster-16 scans (which = 0: forward 16-row slabs, 1: 32 rows, 3: 48 rows, 2: backward)
 int p2pvg_lstm_cluster512_max_clusters_impl(int which) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CS * 64);
@@ -435,6 +457,11 @@ int p2pvg_lstm_cluster512_max_clusters_impl(int which) {
     cudaFuncSetAttribute(lstm_cl16_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(2));
     cudaFuncSetAttribute(lstm_cl16_fwd_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     e = cudaOccupancyMaxActiveClusters(&n, lstm_cl16_fwd_kernel<2>, &cfg);
+  } else if (which == 3) {
+    cfg.dynamicSmemBytes = fwd_smem(3);
+    cudaFuncSetAttribute(lstm_cl16_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(3));
+    cudaFuncSetAttribute(lstm_cl16_fwd_kernel<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaOccupancyMaxActiveClusters(&n, lstm_cl16_fwd_kernel<3>, &cfg);
   } else {
     cfg.dynamicSmemBytes = bwd_smem();
     cudaFuncSetAttribute(lstm_cl16_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem());
@@ -445,12 +472,37 @@ int p2pvg_lstm_cluster512_max_clusters_impl(int which) {
   return n;
 }
 
-// rows per slab of the forward scan: 32 above this batch size (8 clusters of 16 CTAs = one wave for 256 rows)
+// Rows per slab of the forward scan.  Only `maxc` clusters of 16 CTAs are resident at a time (7 on a B200: one per 20-SM GPC),
+// a launch with more clusters runs in waves, each wave a complete pass over the S timesteps.  One timestep of a 16*MT-row slab
+// costs about 1.5 + 2.8*MT us (measured: 4.3 / 7.1 us for MT = 1 / 2; barrier + L2 round trip, then MMA + pointwise per m16
+// tile): pick the MT with the smallest waves * step time.  B = 256: 6 clusters of 48 rows, one wave.
+static int fwd_slab_tiles(int B) {
+  static int maxc = 0, forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("P2PVG_LSTM512_MT");
+    forced = e ? atoi(e) : 0;
+    if (forced < 0 || forced > 3) forced = 0;
+    maxc = p2pvg_lstm_cluster512_max_clusters_impl(1);
+    if (maxc <= 0) maxc = 7;
+  }
+  if (forced) return forced;
+  int best = 1;
+  float best_cost = 0.f;
+  for (int mt = 1; mt <= 3; mt++) {
+    const int clusters = cdiv(B, 16 * mt), waves = cdiv(clusters, maxc);
+    const float cost = waves * (1.5f + 2.8f * mt);
+    if (mt == 1 || cost < best_cost) best = mt, best_cost = cost;
+  }
+  return best;
+}
+
 int p2pvg_lstm_cluster512_fwd_impl(const float* pre, const float* whh, const float* bhh, float* gates, float* hs, float* cs, int S, int B,
                                    cudaStream_t st) {
   if (S <= 0 || B <= 0) return P2PVG_OK;
-  static bool a1 = false, a2 = false;
-  if (B > 128) return launch_cluster16(lstm_cl16_fwd_kernel<2>, "lstm_cl16_fwd", CS * cdiv(B, 32), fwd_smem(2), st, a2, pre, whh, bhh, gates, hs, cs, S, B);
+  static bool a1 = false, a2 = false, a3 = false;
+  const int mt = fwd_slab_tiles(B);
+  if (mt == 3) return launch_cluster16(lstm_cl16_fwd_kernel<3>, "lstm_cl16_fwd", CS * cdiv(B, 48), fwd_smem(3), st, a3, pre, whh, bhh, gates, hs, cs, S, B);
+  if (mt == 2) return launch_cluster16(lstm_cl16_fwd_kernel<2>, "lstm_cl16_fwd", CS * cdiv(B, 32), fwd_smem(2), st, a2, pre, whh, bhh, gates, hs, cs, S, B);
   return launch_cluster16(lstm_cl16_fwd_kernel<1>, "lstm_cl16_fwd", CS * cdiv(B, 16), fwd_smem(1), st, a1, pre, whh, bhh, gates, hs, cs, S, B);
 }
 

@@ -12,7 +12,8 @@ def K():
 
 
 @pytest.mark.parametrize("tf32", [False, True])
-@pytest.mark.parametrize("S,B,R", [(5, 3, 64), (7, 70, 256), (30, 256, 256), (4, 100, 128), (6, 40, 512), (9, 256, 512), (1, 17, 512)])
+@pytest.mark.parametrize("S,B,R", [(5, 3, 64), (7, 70, 256), (30, 256, 256), (4, 100, 128), (6, 40, 512), (9, 256, 512), (1, 17, 512),
+                                   (5, 128, 512), (7, 250, 512), (3, 300, 512)])
 def test_scan_fwd_bwd(K, S, B, R, tf32):
     if R == 512 and not tf32 and B > 128:
         pytest.skip("exact-fp32 R=512 uses the per-step kernels at this batch (the cooperative grid does not fit)")
@@ -57,3 +58,35 @@ def test_scan_fwd_bwd(K, S, B, R, tf32):
     ref = pre_a.grad
     err = (dG.double() - ref).abs().max().item()
     assert err <= tol * ref.abs().max().item() + tol * 0.1, err
+
+
+def test_scan512_slab_size_invariance(K):
+    """The R=512 forward scan picks 16-, 32- or 48-row slabs per cluster from the batch size (one wave of resident clusters);
+    a batch row's result must not depend on that choice: rows 0..39 of a 256-row launch (48-row slabs, partial sums aliased
+    onto the consumed h slab) are bit-identical to the same rows launched alone (16-row slabs), and so are rows of a 128-row
+    launch (32-row slabs)."""
+    S, R = 6, 512
+    torch.manual_seed(3)
+    dev = "cuda"
+    pre = torch.randn(S, 256, 4 * R, device=dev) * 0.5
+    whh = torch.randn(4 * R, R, device=dev) * (1.0 / R ** 0.5)
+    bhh = torch.randn(4 * R, device=dev) * 0.1
+    c0 = torch.randn(256, R, device=dev) * 0.3
+    h0 = torch.randn(256, R, device=dev) * 0.3
+
+    def run(rows):
+        B = len(rows)
+        p = pre[:, rows].contiguous()
+        gates = torch.empty(S, B, 4 * R, device=dev)
+        hs = torch.zeros(S + 1, B, R, device=dev)
+        cs = torch.zeros(S + 1, B, R, device=dev)
+        hs[0], cs[0] = h0[rows], c0[rows]
+        ctr = torch.zeros(4, dtype=torch.int32, device=dev)
+        K.lstm_scan_fwd(p, whh, bhh, gates, hs, cs, S, B, R, ctr, tf32=True)
+        return gates, hs, cs
+
+    full = run(list(range(256)))
+    for rows in (list(range(40)), list(range(100, 228)), list(range(216, 256))):
+        part = run(rows)
+        for a, b, nm in zip(full, part, ("gates", "h", "c")):
+            assert torch.equal(a[:, rows], b), f"{nm}: rows {rows[0]}..{rows[-1]} depend on the slab size"
