@@ -150,6 +150,7 @@ class P2PModel(nn.Module):
         adt = torch.float32 if self.precision == "fp32" else torch.bfloat16
         cls = {"mlp": TrainEngineMLP, "vgg": TrainEngineVGG}.get(cfg["backbone"], TrainEngine)
         eng = cls(state, cfg, self._opt_dict(), kernels_for(dev), act_dtype=adt, mode=self.update_mode)
+        self._grad_views = []
         for m in MODULES:
             mod = getattr(self, m)
             named = list(mod.named_parameters())
@@ -160,6 +161,7 @@ class P2PModel(nn.Module):
                 owner, _, leaf = k.rpartition(".")
                 mod.get_submodule(owner)._buffers[leaf] = eng.buffers[m][k]
             getattr(self, m + "_optimizer").attach(eng.arena[m], named)
+            self._grad_views += [(p, eng.arena[m].g[k]) for k, p in named]
         self._engine = eng
         return eng
 
@@ -173,10 +175,11 @@ class P2PModel(nn.Module):
         eng = self.engine(int(x.shape[-1]))
         eng.opt = self._opt_dict()
         out = eng.step(x.float(), use_graph=self.use_graph, return_device=True)
+        # model.zero_grad() drops .grad; keep them readable for train.py's histograms.  The views are static, so this host work
+        # is done while the GPU runs the step, BEFORE the blocking read-back of the four scalars
+        for p, g in self._grad_views:
+            p.grad = g
         host = out.cpu().numpy()
-        for m in MODULES:  # model.zero_grad() drops .grad; keep them readable for train.py's histograms
-            for k, p in getattr(self, m).named_parameters():
-                p.grad = eng.arena[m].g[k]
         return host[0], host[1], host[2], host[3]
 
     def p2p_generate(self, x, len_output, eval_cp_ix, start_ix=0, cp_ix=-1, model_mode='full', skip_frame=False,

@@ -103,6 +103,11 @@ class EmuKernels:
             r = r + d.float()
         d.copy_(r.to(dst.dtype))
 
+    def nchw_to_nhwc_dual(self, src, dst_f32, dst_act, N, hw, C):
+        for d in (dst_f32, dst_act):
+            if d is not None:
+                self.permute4(src, d, (N, hw, C, 1), (C * hw, 1, hw, 0))
+
     def add_indexed(self, dst, src, dst_idx, F_, n):
         d = _flat(dst, dst.numel()).reshape(-1, n) if dst.numel() % n == 0 else None
         s = _flat(src, F_ * n).reshape(F_, n).float()
