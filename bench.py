@@ -412,6 +412,9 @@ def main():
     barrier()
     e2e_detail = dict(ms_per_step=ms2.item() / args.steps, ms_per_step_batch_resident=ms3.item() / args.steps,
                       host_enqueue_ms_per_step=host_enqueue_ms,
+                      loss_readback=("early: four scalars + sequence number stored to page-locked host memory right after the loss "
+                                     "finalisation and polled by P2PModel.forward; the backward passes / optimiser of step i overlap the "
+                                     "host work of step i+1" if eng.early_loss else "blocking device-to-host copy after the whole step"),
                       note="ms_per_step_batch_resident - device-timed ms_per_step = per-step host + sync latency; "
                            "ms_per_step - ms_per_step_batch_resident = exposed part of the H2D copy")
 
@@ -526,7 +529,7 @@ def main():
                     dtype=("bf16" if args.precision == "bf16" else "f32"), data="synthetic",
                     config=config_dict(c, args.config, T, B, world, args.skip_prob, use_graph, args.strong),
                     roofline=roof, roofline_lstm=roof_lstm, phases_ms=phases, cpu_baseline=cpu, library_baseline=lib,
-                    e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=int(x_host.numel() * 4), d2h_bytes_per_step=16,
+                    e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=int(x_host.numel() * 4), d2h_bytes_per_step=20 if eng.early_loss else 16,
                              detail=e2e_detail),
                     gpu_launches=int(launches), executed_timesteps_per_step=executed / args.steps, clocks=clocks,
                     losses=[float(v) for v in losses])

@@ -149,7 +149,7 @@ int p2pvg_col2im_k4s2p1(const void* col, const void* col2, const int* grp_src, i
 /* dst (contiguous, dims[4]) = src gathered with per-destination-dimension strides (weight packing, NCHW->NHWC, casts). */
 int p2pvg_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims /*host*/,
                    const int64_t* src_strides /*host*/, int accumulate, void* stream);
-/* Frames x [N, C, H*W] fp32 (the layout data/*.py hands to P2PModel.forward, models/p2p_model.py:185-197) -> channels-last
+/* Frames x [N, C, H*W] fp32 (the layout the data loaders hand to P2PModel.forward, models/p2p_model.py:185-197) -> channels-last
  * [N, H*W, C], written once in fp32 (dst_f32: the MSE target, may be NULL) and once in the activation dtype (dst_act: input
  * of the first convolution, may be NULL) from a single read.  C in {2,3,4}, H*W % 4 == 0; one-channel frames need no
  * conversion (NCHW == NHWC). */
@@ -259,6 +259,12 @@ int p2pvg_mse_plain(const float* pred, const float* x, const int* tgt, const flo
 /* the four scalars returned by P2PModel.forward (models/p2p_model.py:271): out[0..3] = mse,kld,cpc,align (/seq_len). */
 int p2pvg_finalize_losses(const float* mse_partial, int n_recon, int has_cpc, double E, const float* kl_sum, float batch_size,
                           const float* align_partial, int n_align, float seq_len, float* out, void* stream);
+/* Early read-back of the step's scalars (models/p2p_model.py:271 returns them as host numbers: `mse.data.cpu().numpy()`): the
+ * kernel stores src[0..n) and then *seq into page-locked, device-mapped host memory host_mapped[0..n] (n floats + one int);
+ * the host polls host_mapped[n] for the sequence number it wrote to *seq before launching.  The values are final once the
+ * forward pass is done, so the caller gets them while the backward passes and the optimiser of the same step still run;
+ * everything else stays stream-ordered.  n <= 64. */
+int p2pvg_publish_scalars(const float* src, int n, float* host_mapped, const int* seq, void* stream);
 /* optim.Adam.step of PyTorch 1.0 (README.md:62; models/p2p_model.py:273-280) on a flat parameter arena. */
 int p2pvg_adam_legacy(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                       double eps, const int* step_ptr, void* stream);

@@ -356,6 +356,10 @@ class CudaKernels:
     def mse_plain(self, pred, x, tgt, coef, G, E, d_pred, partial):
         self._ck(self.lib.p2pvg_mse_plain(_p(pred), _p(x), _p(tgt), _p(coef), _i(G), _i64(E), _p(d_pred), _p(partial), self._stream()))
 
+    def publish_scalars(self, src, n, host_pinned, seq):
+        """src[0..n) + *seq -> page-locked host memory (zero-copy store from the device)"""
+        self._ck(self.lib.p2pvg_publish_scalars(_p(src), _i(n), _vp(host_pinned.data_ptr()), _p(seq), self._stream()))
+
     def finalize_losses(self, mse_partial, n_recon, has_cpc, E, kl_sum, batch_size, align_partial, n_align, seq_len, out):
         self._ck(self.lib.p2pvg_finalize_losses(_p(mse_partial), _i(n_recon), _i(int(has_cpc)), _d(float(E)), _p(kl_sum),
                                                 _f(batch_size), _p(align_partial), _i(n_align), _f(seq_len), _p(out),

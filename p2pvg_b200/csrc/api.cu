@@ -99,6 +99,7 @@ int p2pvg_act_bwd_impl(const float*, const float*, float*, long long, int, cudaS
 int p2pvg_mse_chunks_impl();
 int p2pvg_sigmoid_mse_impl(const void*, int, const float*, const int*, const float*, int, long long, void*, void*, float*, cudaStream_t);
 int p2pvg_finalize_losses_impl(const float*, int, int, double, const float*, float, const float*, int, float, float*, cudaStream_t);
+int p2pvg_publish_scalars_impl(const float*, int, float*, const int*, cudaStream_t);
 int p2pvg_convt_c1_loss_impl(const void*, const void*, int, const int*, const float*, const float*, const int*, const float*, int, int, int, int,
                              int, void*, float*, cudaStream_t);
 int p2pvg_adam_legacy_impl(float*, const float*, float*, float*, long long, double, double, double, double, const int*, cudaStream_t);
@@ -339,6 +340,9 @@ int p2pvg_sigmoid_mse(const void* raw, int dtype, const float* x, const int* tgt
 int p2pvg_finalize_losses(const float* mse_partial, int n_recon, int has_cpc, double E, const float* kl_sum, float batch_size,
                           const float* align_partial, int n_align, float seq_len, float* out, void* stream) {
   return p2pvg_finalize_losses_impl(mse_partial, n_recon, has_cpc, E, kl_sum, batch_size, align_partial, n_align, seq_len, out, ST);
+}
+int p2pvg_publish_scalars(const float* src, int n, float* host_mapped, const int* seq, void* stream) {
+  return p2pvg_publish_scalars_impl(src, n, host_mapped, seq, ST);
 }
 int p2pvg_adam_legacy(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                       double eps, const int* step_ptr, void* stream) {

@@ -117,6 +117,15 @@ __global__ void finalize_losses_kernel(const float* __restrict__ mse_partial, in
   out[3] = (float)(al / seq_len);
 }
 
+// n scalars + a sequence number to page-locked host memory (zero-copy store): the host polls the sequence number, so the
+// values reach it while the rest of the stream (backward passes, optimiser) is still running
+__global__ void publish_scalars_kernel(const float* __restrict__ src, int n, float* host, const int* __restrict__ seq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < n; i++) reinterpret_cast<volatile float*>(host)[i] = src[i];
+  __threadfence_system();
+  reinterpret_cast<volatile int*>(host)[n] = seq[0];
+}
+
 // torch-1.0 Adam: denom = sqrt(v) + eps; p -= lr*sqrt(bc2)/bc1 * m/denom
 __global__ void adam_legacy_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                    long long n, double beta1_d, double beta2_d, double eps_d, double lr,
@@ -180,6 +189,15 @@ int p2pvg_finalize_losses_impl(const float* mse_partial, int n_recon, int has_cp
   finalize_losses_kernel<<<1, 32, 0, st>>>(mse_partial, n_recon, has_cpc, MSE_CHUNKS, E, kl_sum, batch_size, align_partial, n_align,
                                            seq_len, out);
   return p2pvg_check_launch("finalize_losses");
+}
+
+int p2pvg_publish_scalars_impl(const float* src, int n, float* host_mapped, const int* seq, cudaStream_t st) {
+  if (n <= 0 || n > 64 || !src || !host_mapped || !seq) {
+    p2pvg_set_error("publish_scalars: bad arguments");
+    return P2PVG_ERR_BAD_ARG;
+  }
+  publish_scalars_kernel<<<1, 32, 0, st>>>(src, n, host_mapped, seq);
+  return p2pvg_check_launch("publish_scalars");
 }
 
 int p2pvg_adam_legacy_impl(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,

@@ -18,6 +18,8 @@ device data happens inside those kernels.
 from __future__ import annotations
 
 import math
+import os
+import time
 from collections import OrderedDict
 
 import numpy as np
@@ -204,6 +206,16 @@ class TrainEngine:
         self.concurrent = getattr(kernels, "name", "") == "cuda" and act_dtype == torch.bfloat16 and os.environ.get("P2PVG_CONCURRENT", "1") != "0" \
             and os.environ.get("P2PVG_LSTM_CLUSTER", "1") != "0"   # (the cooperative-grid scans must not share the GPU with a second grid-barrier kernel)
         self.streams, self._dirty, self._serial = {}, set(), False
+        # early read-back of the four scalars (P2PModel.forward): zero-copy store into page-locked host memory right after the
+        # loss finalisation, polled by the host while the rest of the step is still running
+        self.early_loss = getattr(kernels, "name", "") == "cuda" and hasattr(kernels, "publish_scalars") \
+            and os.environ.get("P2PVG_EARLY_LOSS", "1") != "0"
+        self._pub_seq = 0
+        if self.early_loss:
+            self._pub_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+            self._pub_np = self._pub_host.numpy()
+            self._pub_seq_np = self._pub_np.view(np.int32)
+            self._pub_seq_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.last_plan = None
         self.phase_events = None
 
@@ -414,12 +426,39 @@ class TrainEngine:
         if ukey != self._uploaded:
             self.upload_plan(plan)
             self._uploaded = ukey
+        if self.early_loss:
+            self._pub_seq = (self._pub_seq + 1) & 0x3FFFFFFF
+            self._pub_seq_dev.fill_(self._pub_seq)
         if use_graph:
             out = self._step_graphed(x, eps, plan)
         else:
             self.eps = eps.contiguous()
             out = self._run(x, plan)
         return out if return_device else out.cpu().numpy()
+
+    def read_losses(self, out):
+        """The four scalars of the step just enqueued, as a host numpy array.  With the early read-back the call returns as soon
+        as the forward half of the step has produced them (the backward passes / optimiser keep running; all later work is
+        stream-ordered behind them); otherwise it is a blocking device-to-host copy of `out`."""
+        if not self.early_loss:
+            return out.cpu().numpy()
+        seq, flag, t0, spins = self._pub_seq, self._pub_seq_np, time.perf_counter(), 0
+        stream = torch.cuda.current_stream(self.dev)
+        while flag[4] != seq:
+            spins += 1
+            if spins & 0x3FF == 0 and time.perf_counter() - t0 > 2e-3:
+                # not there after 2 ms of spinning: make sure the stream is still alive (a failed kernel must raise, not hang)
+                if stream.query():
+                    if flag[4] == seq:
+                        break
+                    torch.cuda.synchronize(self.dev)   # surfaces a sticky CUDA error if there is one
+                    if flag[4] != seq:
+                        return out.cpu().numpy()        # the step ran without the publish kernel (foreign replay): plain read-back
+                    break
+                if time.perf_counter() - t0 > 300.0:
+                    raise RuntimeError("p2pvg_b200: loss read-back timed out")
+                time.sleep(0)
+        return self._pub_np[:4].copy()
 
     def _step_graphed(self, x, eps, plan):
         """CUDA-graph replay of the whole step.  The first call with a new (T,B,S,...) signature runs eagerly
@@ -1060,6 +1099,8 @@ class TrainEngine:
         E = B * self.frame_elems
         K.finalize_losses(self.mse_partial, S, plan.has_cpc, E, self.kl_sum, float(opt["batch_size"]), self.align_partial,
                           max(S - 1, 0), float(T), self.loss_out)
+        if self.early_loss:
+            K.publish_scalars(self.loss_out, 4, self._pub_host, self._pub_seq_dev)
 
     def backward_recurrent(self, plan):
         """Backward #1 through the three LSTMs: d h_pred -> frame predictor -> (z) -> posterior / prior -> dH."""

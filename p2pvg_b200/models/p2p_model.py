@@ -179,7 +179,10 @@ class P2PModel(nn.Module):
         # is done while the GPU runs the step, BEFORE the blocking read-back of the four scalars
         for p, g in self._grad_views:
             p.grad = g
-        host = out.cpu().numpy()
+        # the scalars are final after the forward half of the step: the engine hands them over as soon as they exist (zero-copy
+        # store polled by the host) while the backward passes and the optimiser still run; any later use of the model is
+        # stream-ordered behind them (P2PVG_EARLY_LOSS=0: blocking read-back after the whole step)
+        host = eng.read_losses(out)
         return host[0], host[1], host[2], host[3]
 
     def p2p_generate(self, x, len_output, eval_cp_ix, start_ix=0, cp_ix=-1, model_mode='full', skip_frame=False,

@@ -86,6 +86,35 @@ def test_graph_replay_equals_eager():
         np.testing.assert_allclose(a, b, rtol=2e-3)
 
 
+def test_early_loss_readback_equals_blocking_readback():
+    """P2PModel.forward hands the four scalars over as soon as the forward half of the step has produced them (zero-copy store
+    polled by the host, the backward passes / optimiser still running).  They must be the very numbers a blocking read-back
+    after the whole step gives, for eager steps, the capture step and graph replays; and everything the caller does afterwards
+    (here: reading the weights) must see the finished step (stream order)."""
+    T, B = 4, 4
+    x = torch.rand(T, B, 1, 64, 64, generator=torch.Generator().manual_seed(8)).cuda()
+    runs = {}
+    for early in ("1", "0"):
+        os.environ["P2PVG_EARLY_LOSS"] = early
+        try:
+            model = make_model(B, precision="bf16", graph="1")
+            res = []
+            for it in range(5):
+                torch.manual_seed(70 + it)
+                out = np.array(model(x, 0, T - 1), dtype=np.float32)
+                eng = model._engine
+                assert eng.early_loss == (early == "1")
+                torch.cuda.synchronize()
+                assert np.array_equal(out, eng._bufs["loss_out"][:4].cpu().numpy()), (early, it)
+                res.append((out, model.decoder.state_dict()["upc1.0.weight"].float().sum().item()))
+            runs[early] = res
+        finally:
+            os.environ.pop("P2PVG_EARLY_LOSS", None)
+    for (a, wa), (b, wb) in zip(runs["1"], runs["0"]):
+        np.testing.assert_allclose(a, b, rtol=1e-5)
+        assert abs(wa - wb) <= 1e-5 * abs(wb)
+
+
 def test_module_forwards_match_oracle():
     os.environ["P2PVG_PRECISION"] = "fp32"
     model = make_model(2)
