@@ -379,7 +379,7 @@ def main():
         call(xb)
     barrier()
     e0.record()
-    pf = DevicePrefetcher(host_batches(args.steps), dev)
+    pf = DevicePrefetcher(host_batches(args.steps), dev, early_release=True)   # one train step per batch, nothing else reads it
     for xb in pf:
         losses = call(xb)
         pf.release()

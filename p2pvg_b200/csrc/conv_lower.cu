@@ -197,6 +197,15 @@ __global__ void permute4_kernel(const TS* __restrict__ src, TD* __restrict__ dst
   }
 }
 
+// flat copy / cast (permute4 with one contiguous dimension): 4 elements per thread, 16-byte accesses on the wider side
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) cast_flat4_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const f4 v = ld_f4<TS>(src + i * 4);
+    st_f4<TD>(dst + i * 4, v);
+  }
+}
+
 // ---- frames NCHW fp32 -> NHWC, both precisions from one read: the fp32 copy is the MSE target, the activation-dtype copy
 // feeds the first convolution.  One thread = 4 consecutive pixels of one frame: C float4 plane loads (coalesced per
 // plane), 4*C contiguous outputs.
@@ -376,6 +385,25 @@ int p2pvg_permute4_impl(const void* src, int src_dtype, void* dst, int dst_dtype
     total *= dims[i];
   }
   if (total == 0) return P2PVG_OK;
+  // the frequent special case "cast a contiguous buffer" (e.g. the bf16 operand copies of the LSTM weight-gradient GEMMs)
+  const bool flat = !accumulate && total % 4 == 0 && (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0 &&
+                    ((p.d[1] == 1 && p.d[2] == 1 && p.d[3] == 1 && p.s[0] == 1) ||
+                     (p.d[0] == 1 && p.d[2] == 1 && p.d[3] == 1 && p.s[1] == 1));
+  if (flat) {
+    const long long n4 = total / 4;
+    const int gf = grid_for(n4, 256);
+#define LF(TS, TD) cast_flat4_kernel<TS, TD><<<gf, 256, 0, st>>>((const TS*)src, (TD*)dst, n4)
+    if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_F32) LF(float, float);
+    else if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_BF16) LF(float, bf16);
+    else if (src_dtype == P2PVG_BF16 && dst_dtype == P2PVG_F32) LF(bf16, float);
+    else if (src_dtype == P2PVG_BF16 && dst_dtype == P2PVG_BF16) LF(bf16, bf16);
+    else {
+      p2pvg_set_error("permute4: bad dtypes");
+      return P2PVG_ERR_BAD_ARG;
+    }
+#undef LF
+    return p2pvg_check_launch("permute4 (flat)");
+  }
   int g = grid_for(total, 256);
 #define L(TS, TD) permute4_kernel<TS, TD><<<g, 256, 0, st>>>((const TS*)src, (TD*)dst, p, accumulate)
   if (src_dtype == P2PVG_F32 && dst_dtype == P2PVG_F32) L(float, float);

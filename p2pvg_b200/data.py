@@ -19,7 +19,13 @@ def _chain_front(first, rest):
 
 
 class DevicePrefetcher:
-    def __init__(self, batches, device, depth: int = 2):
+    def __init__(self, batches, device, depth: int = 2, early_release: bool = False):
+        """early_release: the batch handed out is used by exactly ONE train step (``model(x, ...)``) and by nothing after it.
+        The CUDA-graph step copies its input into a static buffer first thing and reports that moment, so the slot can be
+        refilled while that step still runs (two steps of slack for the H2D copy instead of one).  Leave it off when the
+        batch is used again after the step (plots, a second model)."""
+        self.early_release = bool(early_release)
+        self._handout = 0
         self.it = iter(batches)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -87,8 +93,21 @@ class DevicePrefetcher:
         # the slot is simply not re-issued before release (depth >= 2 keeps one batch in flight meanwhile)
         self.free_ev[k] = None
         self._pending_release = k
+        # a consumer that copies the batch away at once (the CUDA-graph train step: static input buffer) reports the moment
+        # through this hook; the slot is then refillable long before the step ends
+        self._handout += 1
+        if self.early_release:
+            x._p2pvg_on_consumed = lambda ev, k=k, tok=self._handout: self._consumed(k, tok, ev)
+        elif hasattr(x, "_p2pvg_on_consumed"):
+            del x._p2pvg_on_consumed
         self._fill()          # start copying the next batch before the caller blocks on this step's results
         return x
+
+    def _consumed(self, k, tok, ev):
+        if self._pending_release == k and self._handout == tok:
+            self._pending_release = None
+            self.free_ev[k] = ev
+            self._fill()
 
     def release(self):
         """Record that everything enqueued so far on the compute stream has consumed the last batch.  Called

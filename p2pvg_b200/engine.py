@@ -372,14 +372,16 @@ class TrainEngine:
         else:
             self.K.gemm(dY, self.arena[m].p[name], out, rows, in_dim, out_dim, b_mn=True, **kw)
 
-    def lin_wgrad(self, dY, X, gW, rows, out_dim, in_dim, ldx=None):
-        """gW[out_dim,in_dim] = dY[rows,out_dim]^T . X[rows,in_dim(+pad)]  (reduction over rows)"""
+    def lin_wgrad(self, dY, X, gW, rows, out_dim, in_dim, ldx=None, reuse_dy=False):
+        """gW[out_dim,in_dim] = dY[rows,out_dim]^T . X[rows,in_dim(+pad)]  (reduction over rows).  reuse_dy: the previous
+        lin_wgrad call on this lane had the same dY (W_hh then W_ih of one LSTM layer): its bf16 copy is still in place."""
         K = self.K
         ldx = ldx or in_dim
         if self.tc_lstm and out_dim % 8 == 0 and ldx % 8 == 0:
             a = self.lbuf("wg_castA", rows * out_dim, torch.bfloat16)
             b = self.lbuf("wg_castB", rows * ldx, torch.bfloat16)
-            K.permute4(dY, a, (rows * out_dim, 1, 1, 1), (1, 0, 0, 0))
+            if not reuse_dy:
+                K.permute4(dY, a, (rows * out_dim, 1, 1, 1), (1, 0, 0, 0))
             K.permute4(X, b, (rows * ldx, 1, 1, 1), (1, 0, 0, 0))
             K.gemm(a, b, gW, out_dim, in_dim, rows, a_mn=True, b_mn=True, lda=out_dim, ldb=ldx)
         else:
@@ -473,6 +475,13 @@ class TrainEngine:
         xs = self.fbuf("x_static", x.numel()).view(-1)[:x.numel()].view(x.shape)
         es = self.fbuf("eps_static", eps.numel()).view(-1)[:eps.numel()].view(eps.shape)
         xs.copy_(x, non_blocking=True)
+        # the caller's batch tensor is not read again by this step: an input pipeline that attached a callback
+        # (p2pvg_b200.data.DevicePrefetcher) may refill its slot from here on instead of after the whole step
+        consumed = getattr(x, "_p2pvg_on_consumed", None)
+        if consumed is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            consumed(ev)
         es.copy_(eps, non_blocking=True)
         self.eps = es
         st = self._graphs.get(key)
@@ -1051,7 +1060,7 @@ class TrainEngine:
             if want_wgrad:
                 with self.fork(self.LANE_WGRAD):   # off the critical path: nothing below reads a weight gradient
                     self.lin_wgrad(dG, lay["hs"], A.g[f"lstm.{l}.weight_hh"], rows, 4 * R, R)
-                    self.lin_wgrad(dG, lay["inp"], A.g[f"lstm.{l}.weight_ih"], rows, 4 * R, R)
+                    self.lin_wgrad(dG, lay["inp"], A.g[f"lstm.{l}.weight_ih"], rows, 4 * R, R, reuse_dy=True)
                     K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_ih"])
                     K.colsum(dG, rows, 4 * R, 4 * R, A.g[f"lstm.{l}.bias_hh"])
             dIn = self.fbuf(f"{m}_dIn{l}", rows * R)

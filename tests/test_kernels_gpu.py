@@ -167,6 +167,22 @@ def test_permute4(KS, sd, dd):
     assert torch.equal(d2.float().reshape(6, 4, 4, 5)[:, 1, 2, 3], (2 * w.float()[:, 3, 1, 2]).to(dd).float())
 
 
+@pytest.mark.parametrize("sd,dd", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.float32), (torch.float32, torch.float32),
+                                   (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("n", [4 * 1000 + 0, 4 * 1000 + 3, 1 << 20])
+def test_permute4_flat_cast(KS, sd, dd, n):
+    """contiguous copy / cast (the bf16 operand copies of the LSTM weight-gradient GEMMs): 16-byte-vector path when the length
+    is a multiple of 4, generic path otherwise; both are exact round-to-nearest casts"""
+    Kc, _ = KS
+    src = rnd(n, dtype=sd, seed=9)
+    dst = torch.zeros(n + 8, device="cuda", dtype=dd)
+    Kc.permute4(src, dst, (n, 1, 1, 1), (1, 0, 0, 0))
+    assert torch.equal(dst[:n], src.to(dd)) and not dst[n:].any()
+    dst.zero_()
+    Kc.permute4(src, dst, (1, n, 1, 1), (0, 1, 0, 0))
+    assert torch.equal(dst[:n], src.to(dd)) and not dst[n:].any()
+
+
 @pytest.mark.parametrize("C", [2, 3, 4])
 @pytest.mark.parametrize("adt", [torch.bfloat16, torch.float32, None])
 def test_nchw_to_nhwc_dual(KS, C, adt):
