@@ -98,23 +98,28 @@ __global__ void __launch_bounds__(256) convt_c1_loss_kernel(const T* __restrict_
 __global__ void finalize_losses_kernel(const float* __restrict__ mse_partial, int n_recon, int has_cpc, int nchunk, double E,
                                        const float* __restrict__ kl_sum, float batch_size, const float* __restrict__ align_partial,
                                        int n_align, float seq_len, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: lane k sums chunk column k of every group (independent loads in flight instead of one thread's dependent chain of
+  // n_recon * nchunk), fp64, combined by a fixed shuffle tree (deterministic)
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0 || lane >= 32) return;
   double mse = 0.0, cpc = 0.0, al = 0.0;
-  for (int g = 0; g < n_recon; g++) {
-    double s = 0.0;
-    for (int k = 0; k < nchunk; k++) s += (double)mse_partial[g * nchunk + k];
-    mse += s / E;
+  for (int k = lane; k < nchunk; k += 32) {
+    for (int g = 0; g < n_recon; g++) mse += (double)mse_partial[g * nchunk + k];
+    if (has_cpc) cpc += (double)mse_partial[n_recon * nchunk + k];
   }
-  if (has_cpc) {
-    double s = 0.0;
-    for (int k = 0; k < nchunk; k++) s += (double)mse_partial[n_recon * nchunk + k];
-    cpc = s / E;
+  for (int s = lane; s < n_align; s += 32) al += (double)align_partial[s];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mse += __shfl_xor_sync(0xffffffffu, mse, o);
+    cpc += __shfl_xor_sync(0xffffffffu, cpc, o);
+    al += __shfl_xor_sync(0xffffffffu, al, o);
   }
-  for (int s = 0; s < n_align; s++) al += (double)align_partial[s];
-  out[0] = (float)(mse / seq_len);
-  out[1] = (float)((double)kl_sum[0] / batch_size / seq_len);
-  out[2] = (float)(cpc / seq_len);
-  out[3] = (float)(al / seq_len);
+  if (lane == 0) {
+    out[0] = (float)(mse / E / seq_len);
+    out[1] = (float)((double)kl_sum[0] / batch_size / seq_len);
+    out[2] = (float)(cpc / E / seq_len);
+    out[3] = (float)(al / seq_len);
+  }
 }
 
 // n scalars + a sequence number to page-locked host memory (zero-copy store): the host polls the sequence number, so the

@@ -39,14 +39,17 @@ __global__ void lstm_pointwise_bwd_kernel(const float* __restrict__ dh, const fl
   dc_prev[idx] = dc * f;
 }
 
-// z = eps*exp(lv/2)+mu for posterior and prior; KL(N(mu,lv)||N(mu_p,lv_p)) summed (misc/criterion.py:12-15)
-__global__ void __launch_bounds__(1024) reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
-                                                              const float* __restrict__ mu_p, const float* __restrict__ lv_p,
-                                                              const float* __restrict__ eps, const float* __restrict__ eps_p,
-                                                              float* __restrict__ z, float* __restrict__ z_p, int n,
-                                                              float* __restrict__ kl_sum) {
+// z = eps*exp(lv/2)+mu for posterior and prior; KL(N(mu,lv)||N(mu_p,lv_p)) summed (misc/criterion.py:12-15).
+// One thread-block cluster of 8 CTAs: the kernel sits on the critical path between the Gaussian heads and the frame predictor, and a
+// single CTA needs n/1024 dependent trips; the 8 per-CTA partial sums are combined by CTA 0 through distributed shared memory in
+// rank order (deterministic, no workspace, no atomics).
+constexpr int RKL_CTAS = 8;
+__global__ void __cluster_dims__(RKL_CTAS, 1, 1) __launch_bounds__(1024)
+reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ mu_p,
+                      const float* __restrict__ lv_p, const float* __restrict__ eps, const float* __restrict__ eps_p,
+                      float* __restrict__ z, float* __restrict__ z_p, int n, float* __restrict__ kl_sum) {
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float m1 = mu[i], l1 = lv[i], m2 = mu_p[i], l2 = lv_p[i];
     float s1 = expf(0.5f * l1), s2 = expf(0.5f * l2);
     z[i] = eps[i] * s1 + m1;
@@ -56,14 +59,32 @@ __global__ void __launch_bounds__(1024) reparam_kl_fwd_kernel(const float* __res
     acc += (double)k;
   }
   __shared__ double sh[32];
+  __shared__ double cta_sum;
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
     double v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
     v = warp_sum_d(v);
-    if (threadIdx.x == 0) kl_sum[0] = (float)v;
+    if (threadIdx.x == 0) cta_sum = v;
   }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (rank == 0 && threadIdx.x == 0) {
+    double v = 0.0;
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&cta_sum);
+    for (uint32_t r = 0; r < RKL_CTAS; r++) {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      double t;
+      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(t) : "r"(remote) : "memory");
+      v += t;
+    }
+    kl_sum[0] = (float)v;
+  }
+  // nobody may exit while CTA 0 still reads its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ mu_p,
@@ -129,25 +150,43 @@ __global__ void gather_add_cols_kernel(float* __restrict__ dst, const float* __r
 
 // pairs s=0..P-1: loss_s = mean_{b,j} (H[in[s],0,j] - h_pred[s,b,j])^2
 //   d_hpred[s,b,j] += coef*2*(h_pred - h0)/(B*g);   dH[in[s],0,j] += coef*2*sum_b (h0 - h_pred)/(B*g)
-__global__ void align_kernel(const float* __restrict__ H, const int* __restrict__ in_idx, const float* __restrict__ h_pred, int P,
+__global__ void __launch_bounds__(1024) align_kernel(const float* __restrict__ H, const int* __restrict__ in_idx, const float* __restrict__ h_pred, int P,
                              int B, int g, float coef, float* __restrict__ loss_partial, float* __restrict__ d_hpred,
                              float* __restrict__ dH) {
+  // block = one pair s; thread = (column jl of a 128-column pass, row lane of 8): a lane walks rows lane, lane+8, ... so the
+  // dependent read-modify-write chain per thread is B/8 long instead of B; the 8 lanes of a column are combined in a fixed
+  // order (deterministic)
+  constexpr int CW = 128, RL = 8;
   const int s = blockIdx.x;
+  const int jl = threadIdx.x % CW, lane = threadIdx.x / CW;
   const float invn = 1.f / ((float)B * (float)g);
-  double lacc = 0.0;
-  for (int j = threadIdx.x; j < g; j += blockDim.x) {
-    const float h0 = H[((long long)in_idx[s] * B + 0) * g + j];
-    float dsum = 0.f;
-    for (int b = 0; b < B; b++) {
-      long long o = ((long long)s * B + b) * g + j;
-      float diff = h0 - h_pred[o];
-      lacc += (double)diff * (double)diff;
-      dsum += diff;
-      if (d_hpred) d_hpred[o] += -coef * 2.f * diff * invn;
-    }
-    if (dH) dH[((long long)in_idx[s] * B + 0) * g + j] += coef * 2.f * dsum * invn;
-  }
+  __shared__ float dsh[RL][CW];
   __shared__ double sh[32];
+  double lacc = 0.0;
+  const long long hrow = ((long long)in_idx[s] * B + 0) * g;
+  for (int j0 = 0; j0 < g; j0 += CW) {
+    const int j = j0 + jl;
+    float dsum = 0.f;
+    if (j < g) {
+      const float h0 = H[hrow + j];
+      for (int b = lane; b < B; b += RL) {
+        const long long o = ((long long)s * B + b) * g + j;
+        const float diff = h0 - h_pred[o];
+        lacc += (double)diff * (double)diff;
+        dsum += diff;
+        if (d_hpred) d_hpred[o] += -coef * 2.f * diff * invn;
+      }
+    }
+    dsh[lane][jl] = dsum;
+    __syncthreads();
+    if (lane == 0 && j < g && dH) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < RL; l++) t += dsh[l][jl];
+      dH[hrow + j] += coef * 2.f * t * invn;
+    }
+    __syncthreads();
+  }
   lacc = warp_sum_d(lacc);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = lacc;
   __syncthreads();
@@ -229,7 +268,7 @@ int p2pvg_lstm_pointwise_bwd_impl(const float* dh, const float* dc_next, const f
 }
 int p2pvg_reparam_kl_fwd_impl(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,
                               const float* eps_p, float* z, float* z_p, int n, float* kl_sum, cudaStream_t st) {
-  reparam_kl_fwd_kernel<<<1, 1024, 0, st>>>(mu, lv, mu_p, lv_p, eps, eps_p, z, z_p, n, kl_sum);
+  reparam_kl_fwd_kernel<<<RKL_CTAS, 1024, 0, st>>>(mu, lv, mu_p, lv_p, eps, eps_p, z, z_p, n, kl_sum);
   return p2pvg_check_launch("reparam_kl_fwd");
 }
 int p2pvg_reparam_kl_bwd_impl(const float* mu, const float* lv, const float* mu_p, const float* lv_p, const float* eps,
@@ -257,7 +296,7 @@ int p2pvg_gather_add_cols_impl(float* dst, const float* src, const int* idx, int
 int p2pvg_align_impl(const float* H, const int* in_idx, const float* h_pred, int P, int B, int g, float coef, float* loss_partial,
                      float* d_hpred, float* dH, cudaStream_t st) {
   if (P <= 0) return P2PVG_OK;
-  align_kernel<<<P, 128, 0, st>>>(H, in_idx, h_pred, P, B, g, coef, loss_partial, d_hpred, dH);
+  align_kernel<<<P, 1024, 0, st>>>(H, in_idx, h_pred, P, B, g, coef, loss_partial, d_hpred, dH);
   return p2pvg_check_launch("align");
 }
 int p2pvg_colsum_impl(const void* x, int dtype, long long rows, int cols, long long ld, float* out, int accumulate, void* ws,
