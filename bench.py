@@ -379,7 +379,8 @@ def main():
         call(xb)
     barrier()
     e0.record()
-    pf = DevicePrefetcher(host_batches(args.steps), dev, early_release=True)   # one train step per batch, nothing else reads it
+    pf = DevicePrefetcher(host_batches(args.steps), dev, early_release=True,   # one train step per batch, nothing else reads it
+                          copy_streams=int(os.environ.get("P2PVG_BENCH_COPY_STREAMS", "1")))
     for xb in pf:
         losses = call(xb)
         pf.release()
@@ -410,8 +411,25 @@ def main():
     host_enqueue_ms = (time.perf_counter() - th0) / args.steps * 1e3
     torch.cuda.synchronize(dev)
     barrier()
+    # raw host->device rate of this box for the step's input (GPU otherwise idle), one copy at a time and split over
+    # several streams: an exposed H2D copy means the box sustains less than bytes_per_step / ms_per_step
+    def h2d_rate(nstreams, reps=3):
+        streams = [torch.cuda.Stream(dev) for _ in range(nstreams)]
+        dst = torch.empty_like(x_dev)
+        hs, ds = x_host.view(-1).chunk(nstreams), dst.view(-1).chunk(nstreams)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for st, h, d in zip(streams, hs, ds):
+                with torch.cuda.stream(st):
+                    d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return reps * x_host.numel() * x_host.element_size() / (time.perf_counter() - t0) / 1e9
+    h2d_rates = {f"{n}_streams": round(h2d_rate(n), 2) for n in (1, 2, 4)}
+    barrier()
     e2e_detail = dict(ms_per_step=ms2.item() / args.steps, ms_per_step_batch_resident=ms3.item() / args.steps,
-                      host_enqueue_ms_per_step=host_enqueue_ms,
+                      host_enqueue_ms_per_step=host_enqueue_ms, h2d_gbps_gpu_idle=h2d_rates,
+                      h2d_gbps_needed=x_host.numel() * x_host.element_size() / (ms_step * 1e-3) / 1e9,
                       loss_readback=("early: four scalars + sequence number stored to page-locked host memory right after the loss "
                                      "finalisation and polled by P2PModel.forward; the backward passes / optimiser of step i overlap the "
                                      "host work of step i+1" if eng.early_loss else "blocking device-to-host copy after the whole step"),

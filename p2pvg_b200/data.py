@@ -19,7 +19,7 @@ def _chain_front(first, rest):
 
 
 class DevicePrefetcher:
-    def __init__(self, batches, device, depth: int = 2, early_release: bool = False):
+    def __init__(self, batches, device, depth: int = 2, early_release: bool = False, copy_streams: int = 1):
         """early_release: the batch handed out is used by exactly ONE train step (``model(x, ...)``) and by nothing after it.
         The CUDA-graph step copies its input into a static buffer first thing and reports that moment, so the slot can be
         refilled while that step still runs (two steps of slack for the H2D copy instead of one).  Leave it off when the
@@ -30,7 +30,10 @@ class DevicePrefetcher:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher copies to a CUDA device")
-        self.copy_stream = torch.cuda.Stream(self.device)
+        # copy_streams > 1 splits every batch into that many pieces, each copied on its own stream (some hosts reach the link rate
+        # only with several DMA transfers in flight)
+        self.copy_streams = [torch.cuda.Stream(self.device) for _ in range(max(1, int(copy_streams)))]
+        self.copy_stream = self.copy_streams[0]
         self.depth = max(2, int(depth))
         self.slots = [None] * self.depth      # device buffers, reused round-robin
         self.free_ev = [None] * self.depth    # compute-stream event: the slot's previous consumer has been enqueued
@@ -52,20 +55,25 @@ class DevicePrefetcher:
             return False
         self.n += 1
         if not host.is_pinned():  # page-locked staging buffer (reused); pinned inputs are copied from directly
-            if self.copied_ev[k] is not None:
-                self.copied_ev[k].synchronize()   # the previous copy out of this staging buffer must have finished
+            for ev in self.copied_ev[k] or ():
+                ev.synchronize()   # the previous copy out of this staging buffer must have finished
             if self.pinned[k] is None or self.pinned[k].shape != host.shape or self.pinned[k].dtype != host.dtype:
                 self.pinned[k] = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
             self.pinned[k].copy_(host)
             host = self.pinned[k]
         if self.slots[k] is None or self.slots[k].shape != host.shape or self.slots[k].dtype != host.dtype:
             self.slots[k] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
-        with torch.cuda.stream(self.copy_stream):
-            if self.free_ev[k] is not None:
-                self.copy_stream.wait_event(self.free_ev[k])   # do not overwrite a batch the step may still read
-            self.slots[k].copy_(host, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(self.copy_stream)
+        n = len(self.copy_streams) if host.is_contiguous() and host.numel() >= (1 << 20) else 1
+        src, dst = (host.view(-1).chunk(n), self.slots[k].view(-1).chunk(n)) if n > 1 else ((host,), (self.slots[k],))
+        ready = []
+        for st, h, d in zip(self.copy_streams, src, dst):
+            with torch.cuda.stream(st):
+                if self.free_ev[k] is not None:
+                    st.wait_event(self.free_ev[k])   # do not overwrite a batch the step may still read
+                d.copy_(h, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                ready.append(ev)
         self.copied_ev[k] = ready
         self.queue.append((k, ready))
         return True
@@ -87,7 +95,8 @@ class DevicePrefetcher:
             if not self.queue:
                 raise StopIteration
         k, ready = self.queue.pop(0)
-        cur.wait_event(ready)
+        for ev in ready:
+            cur.wait_event(ev)
         x = self.slots[k]
         # until released, the slot must not be refilled: an un-recorded event would not block the copy stream, so
         # the slot is simply not re-issued before release (depth >= 2 keeps one batch in flight meanwhile)

@@ -65,3 +65,18 @@ def test_prefetcher_early_release_through_the_graph_step():
     for i, (u, v) in enumerate(zip(a, b)):
         np.testing.assert_allclose(u, v, rtol=1e-5, err_msg=f"step {i}")
     assert len({tuple(u) for u in a}) == n      # the batches differ, so do the losses
+
+
+@pytest.mark.parametrize("streams", [1, 3])
+def test_prefetcher_chunked_copies(streams):
+    """copy_streams > 1: every batch is split into pieces copied on separate streams; the consumer must see whole batches"""
+    from p2pvg_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(5)
+    host = [torch.rand(3, 5, 1, 300, 300, generator=g).pin_memory() for _ in range(5)]   # 1.35 M elements each
+    got = []
+    pf = DevicePrefetcher(iter(host), "cuda", copy_streams=streams)
+    for x in pf:
+        got.append(x.sum(dtype=torch.float64) + 0)     # consumer work on the current stream, before the slot is refilled
+        pf.release()
+    for a, h in zip(got, host):
+        assert abs(a.item() - h.sum(dtype=torch.float64).item()) < 1e-6 * h.numel()
