@@ -732,9 +732,10 @@ int p2pvg_lstm_cluster512_fwd_impl(const float* pre, const float* whh, const flo
   return launch_cluster16(lstm_cl16_fwd_kernel<1>, "lstm_cl16_fwd", CS * cdiv(B, 16), fwd_smem(1), st, a1, pre, whh, bhh, gates, hs, cs, S, B);
 }
 
-// Rows per slab of the backward scan, same wave model as the forward one.  Measured per timestep: 16-row slabs (weights half in
-// shared memory) 5.4 us; the tensor-memory variants are modelled as 2.6 + 2.8 us per m16 tile until measured (env override
-// P2PVG_LSTM512_BWD_MT = 1 | 2 | 3).
+// Rows per slab of the backward scan, same wave model as the forward one.  Measured per timestep: 16-row slabs (weight half in
+// shared memory) 5.7 us, 32 / 48-row slabs (weight half in tensor memory) 8.0 / 11.1 us, i.e. about 3.0 + 2.7 us per m16 tile;
+// B = 256: one wave of 6 clusters (11.2 us) instead of three waves of 16-row slabs (15.9 us).  Env override
+// P2PVG_LSTM512_BWD_MT = 1 | 2 | 3.
 static int bwd_slab_tiles(int B) {
   static int maxc = 0, forced = -1;
   if (forced < 0) {
@@ -749,7 +750,7 @@ static int bwd_slab_tiles(int B) {
   float best_cost = 0.f;
   for (int mt = 1; mt <= 3; mt++) {
     const int clusters = cdiv(B, 16 * mt), waves = cdiv(clusters, maxc);
-    const float cost = waves * (2.6f + 2.8f * mt);
+    const float cost = waves * (3.0f + 2.7f * mt);
     if (mt == 1 || cost < best_cost) best = mt, best_cost = cost;
   }
   return best;

@@ -26,6 +26,8 @@ for B in (16, 64, 128, 256):
     dh = torch.randn(S, B, R, device=dev)
     ctr = torch.zeros(4, dtype=torch.int32, device=dev)
     for tf32 in (True, False):
+        if not tf32 and R == 512 and B > 128:
+            continue   # exact-fp32 R=512 above 128 rows runs as per-step kernels in the engine (the cooperative grid does not fit)
         res = []
         for which in ("fwd", "bwd"):
             ts = []
