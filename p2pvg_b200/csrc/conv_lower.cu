@@ -386,9 +386,16 @@ int p2pvg_permute4_impl(const void* src, int src_dtype, void* dst, int dst_dtype
   }
   if (total == 0) return P2PVG_OK;
   // the frequent special case "cast a contiguous buffer" (e.g. the bf16 operand copies of the LSTM weight-gradient GEMMs)
-  const bool flat = !accumulate && total % 4 == 0 && (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0 &&
-                    ((p.d[1] == 1 && p.d[2] == 1 && p.d[3] == 1 && p.s[0] == 1) ||
-                     (p.d[0] == 1 && p.d[2] == 1 && p.d[3] == 1 && p.s[1] == 1));
+  // (any gather whose source strides are those of a contiguous tensor of the same dims, size-1 dims ignored)
+  bool dense = true;
+  long long expect = 1;
+  for (int i = 3; i >= 0; i--) {
+    if (p.d[i] == 1) continue;
+    if (p.s[i] != expect) dense = false;
+    expect *= p.d[i];
+  }
+  const bool flat = dense && !accumulate && total % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0;
   if (flat) {
     const long long n4 = total / 4;
     const int gf = grid_for(n4, 256);

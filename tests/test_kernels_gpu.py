@@ -181,6 +181,13 @@ def test_permute4_flat_cast(KS, sd, dd, n):
     dst.zero_()
     Kc.permute4(src, dst, (1, n, 1, 1), (0, 1, 0, 0))
     assert torch.equal(dst[:n], src.to(dd)) and not dst[n:].any()
+    if n % 8 == 0:   # contiguous source described with several dims (one-channel frames: NCHW == NHWC)
+        dst.zero_()
+        Kc.permute4(src, dst, (n // 8, 8, 1, 1), (8, 1, 8, 0))
+        assert torch.equal(dst[:n], src.to(dd)) and not dst[n:].any()
+        dst.zero_()
+        Kc.permute4(src, dst, (n // 8, 2, 4, 1), (8, 1, 2, 0))   # a real permutation of the same data: generic path
+        assert torch.equal(dst[:n], src.view(n // 8, 4, 2).transpose(1, 2).reshape(-1).to(dd))
 
 
 @pytest.mark.parametrize("C", [2, 3, 4])
