@@ -603,12 +603,11 @@ class TrainEngine:
             self._graphs.clear()
         return out
 
-    # -- Phase E ----------------------------------------------------------------------------
-    def encode(self, x, plan):
-        K, T, B, n, nc, W0 = self.K, self.T, self.B, self.n, self.nc, self.W0
-        P = self.arena["encoder"].p
+    def frames_nhwc(self, x):
+        """Frames NCHW fp32 -> NHWC: self.x_nhwc (fp32, the MSE target) and the returned activation-dtype copy (input of the
+        first convolution); multi-channel inputs are converted by one kernel that reads the frames once."""
+        K, T, B, nc, W0 = self.K, self.T, self.B, self.nc, self.W0
         N = T * B
-        # NCHW fp32 -> NHWC (fp32 target for the MSE, act-dtype input of c1)
         hw = W0 * W0
         xs = x.contiguous()
         if nc == 1 and xs.dtype == torch.float32:
@@ -629,6 +628,14 @@ class TrainEngine:
                 K.nchw_to_nhwc_dual(xs, self.x_nhwc, a, N, hw, nc)
             else:
                 K.permute4(xs, a, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
+        return a
+
+    # -- Phase E ----------------------------------------------------------------------------
+    def encode(self, x, plan):
+        K, T, B, n, nc, W0 = self.K, self.T, self.B, self.n, self.nc, self.W0
+        P = self.arena["encoder"].p
+        N = T * B
+        a = self.frames_nhwc(x)
         self.enc_in = a
         self.enc = []
         H = W0

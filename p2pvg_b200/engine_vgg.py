@@ -152,18 +152,7 @@ class TrainEngineVGG(TrainEngine):
         K, T, B, nc = self.K, self.T, self.B, self.nc
         P = self.arena["encoder"].p
         N = T * B
-        hw = self.W0 * self.W0
-        xs = x.contiguous()
-        if nc == 1 and xs.dtype == torch.float32:
-            self.x_nhwc = xs.view(-1)  # one channel: NCHW == NHWC, the MSE target is the input itself
-        else:
-            self.x_nhwc = self.fbuf("x_nhwc", N * hw * nc)
-            K.permute4(xs, self.x_nhwc, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
-        if self.adt == torch.float32:
-            a = self.x_nhwc
-        else:
-            a = self.buf("x_act", N * hw * nc)
-            K.permute4(xs, a, (N, hw, nc, 1), (nc * hw, 1, hw, 0))
+        a = self.frames_nhwc(x)
         self.venc = [[] for _ in self.ENC]
         H, C = self.W0, nc
         for i, j, cin, cout, pre in self.enc_layers():
