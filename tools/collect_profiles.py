@@ -32,33 +32,38 @@ def last_json_line(src, dst):
 
 
 for c in ("C2", "C2_skip", "C3", "C4", "C5"):
-    for job in ("r2j", "r2g", "r2f", "r2e"):   # newest job that has the line
+    for job in ("r2z", "r2j", "r2g", "r2f", "r2e"):   # newest job that has the line
         if os.path.exists(os.path.join(G, job, f"bench_{c}.json")) and os.path.getsize(os.path.join(G, job, f"bench_{c}.json")) > 0:
             last_json_line(f"{job}/bench_{c}.json", f"bench_r02_{c}.json")
             break
-last_json_line("r2j/bench_ref_C2.json" if os.path.exists(os.path.join(G, "r2j/bench_ref_C2.json")) else "r2e/bench_ref_C2.json", "bench_r02_ref_C2.json")
+last_json_line(next((f"{j}/bench_ref_C2.json" for j in ("r2z", "r2j", "r2e") if os.path.exists(os.path.join(G, j, "bench_ref_C2.json"))), "r2e/bench_ref_C2.json"), "bench_r02_ref_C2.json")
 for n in (2, 8):
     for f in glob.glob(os.path.join(G, f"r2m{n}", "bench_*.json")):
         last_json_line(os.path.relpath(f, G), f"bench_r02_N{n}_" + os.path.basename(f)[6:])
     cp(f"r2m{n}/dp_check.log", f"dp_check_r02_N{n}.txt")
 ab = []
-for d in ("r2c", "r2d", "r2e", "r2f", "r2g", "r2h", "r2i"):
+for d in ("r2c", "r2d", "r2e", "r2f", "r2g", "r2h", "r2i", "r2o"):
     f = os.path.join(G, d, "ab.txt" if d < "r2h" else "scan.txt")
     if os.path.exists(f):
         ab.append(f"##### job {d} (one box per job; compare lines within a job only)\n" + open(f).read())
 if ab:
     open(os.path.join(P, "ab_r02.txt"), "w").write("\n".join(ab))
     print("ok   ab_r02.txt")
-cp("r2p/launches_C2.txt", "launches_r02_C2.txt")
-cp("r2p/calls_C2.txt", "calls_r02_C2.txt")
+cp("r2z/launches_C2.txt", "launches_r02_C2.txt")
+cp("r2z/calls_C2.txt", "calls_r02_C2.txt")
+cp("r2p/calls_C2.txt", "calls_r02_C2_before_helper_kernel_fixes.txt")
 cp("r2f/calls_C3.txt", "calls_r02_C3.txt")
 cp("r2p/calls_C3.txt", "calls_r02_C3_before_vectorised_data_movement.txt")
 cp("r2p/scan_R512.txt", "scan_r02_R512_before_48_row_slabs.txt")
-cp("r2h/calls_C4.txt", "calls_r02_C4.txt")
-cp("r2h/calls_C5.txt", "calls_r02_C5.txt")
-cp("r2j/tests_all.log", "tests_gpu_all_r02.txt")
+cp("r2z/calls_C4.txt", "calls_r02_C4.txt")
+cp("r2z/calls_C5.txt", "calls_r02_C5.txt")
+cp("r2h/calls_C5.txt", "calls_r02_C5_before_cast_and_slab_fixes.txt")
+cp("r2z/tests_all.log", "tests_gpu_all_r02.txt")
+cp("r2z/scan_R512.txt", "scan_r02_R512.txt")
+cp("r2m/autocast_vgg.txt", "autocast_context_vgg_r02.txt")
+cp("r2m/autocast_dcgan.txt", "autocast_context_dcgan_r02.txt")
 for rep, out, work in (("r2p/conv_full.ncu-rep", "ncu_conv_r02.txt", ["conv_gemm_kernel=0.503", "convt4_kernel=0.515"]),
-                       ("r2p/lstm_full.ncu-rep", "ncu_lstm_r02.txt", [])):
+                       ("r2z/lstm_full.ncu-rep", "ncu_lstm_r02.txt", [])):
     src = os.path.join(G, rep)
     if os.path.exists(src):
         cmd = [sys.executable, os.path.join(ROOT, "tools", "summarize_ncu.py"), src] + (["--work"] + work if work else [])
