@@ -387,12 +387,14 @@ def test_sigmoid_mse_finalize_adam(KS, dtype):
 
 
 @pytest.mark.parametrize("C", [1, 3])
-def test_convt_c1_loss_equals_col2im_plus_sigmoid_mse(C):
-    """Fused last decoder layer (tap gather + bias + sigmoid + MSE + d raw) against the two-kernel path it replaces."""
+@pytest.mark.parametrize("Hi", [8, 6, 32])
+def test_convt_c1_loss_equals_col2im_plus_sigmoid_mse(C, Hi):
+    """Fused last decoder layer (tap gather + bias + sigmoid + MSE + d raw) against the two-kernel path it replaces.
+    Hi % 4 == 0 runs the shared-memory-staged variant (4-row bands), Hi = 6 the direct-gather one."""
     from p2pvg_b200._lib import CudaKernels
     K = CudaKernels("cuda")
     torch.manual_seed(0)
-    G, B, Hi, nsrc, T = 5, 3, 8, 2, 7
+    G, B, nsrc, T = 5, 3, 2, 7
     N = G * B
     col = (torch.randn(N * Hi * Hi, 16 * C, device="cuda") * 0.5).bfloat16()
     col2 = (torch.randn(nsrc * B * Hi * Hi, 16 * C, device="cuda") * 0.5).bfloat16()
