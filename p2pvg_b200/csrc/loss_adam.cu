@@ -1,8 +1,6 @@
 // Fused sigmoid + MSE (forward value and gradient w.r.t. the pre-sigmoid decoder output in one
 // pass), the loss finaliser that produces the four host-visible scalars of P2PModel.forward
 // (models/p2p_model.py:271), and the flat-arena Adam update with PyTorch-1.0 arithmetic.
-#include <cstdlib>
-
 #include "common.cuh"
 
 #define MSE_CHUNKS 32
@@ -84,88 +82,6 @@ __global__ void __launch_bounds__(256) convt_c1_loss_kernel(const T* __restrict_
       const float d = s - xt[e * C + c];
       acc += (double)d * (double)d;
       st_f<T>(dg + e * C + c, cf * 2.f * d * s * (1.f - s));
-    }
-  }
-  __shared__ double sh[8];
-  acc = warp_sum_d(acc);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double v = 0.0;
-    for (int w = 0; w < 8; w++) v += sh[w];
-    partial[(long long)g * gridDim.x + blockIdx.x] = (float)v;
-  }
-}
-
-// The same fusion with the tap products staged through shared memory: a block walks (frame, 4-input-row band) units of its group;
-// the band's rows of col + col2 (plus one halo row above and below, full image width) are read ONCE with contiguous vector loads,
-// summed in fp32 into shared memory, and the 8 x 2Wi output pixels of the band gather their four taps from there.  The per-pixel
-// gather of the kernel above touches 2*C-byte pieces of 32*C-byte rows in global memory (sector efficiency ~20 %); here every
-// global access is a full coalesced vector.  Arithmetic per output pixel is unchanged ((col + col2) per tap, then the 4-tap sum).
-template <typename T, int C>
-__global__ void __launch_bounds__(256) convt_c1_loss_tiled_kernel(const T* __restrict__ col, const T* __restrict__ col2, const int* __restrict__ grp_src,
-                                                                  const float* __restrict__ bias, const float* __restrict__ x,
-                                                                  const int* __restrict__ tgt, const float* __restrict__ coef, int B, int Hi,
-                                                                  int Wi, T* __restrict__ d_raw, float* __restrict__ partial) {
-  constexpr int TR = 4, RW = 16 * C;          // input rows per band, values per input pixel
-  extern __shared__ __align__(16) float sv[];  // [(TR + 2) rows][Wi][16*C]  col + col2, fp32
-  const int g = blockIdx.y;
-  const unsigned Ho = 2u * Hi, Wo = 2u * Wi;
-  const unsigned P = (unsigned)B * Ho * Wo;
-  const float* xt = x + (long long)tgt[g] * P * C;
-  const T* cg = col + (long long)g * B * Hi * Wi * RW;
-  const T* sg = col2 + (long long)grp_src[g] * B * Hi * Wi * RW;
-  T* dg = d_raw + (long long)g * P * C;
-  const float cf = coef[g];
-  float b0[C];
-#pragma unroll
-  for (int c = 0; c < C; c++) b0[c] = bias ? bias[c] : 0.f;
-  const int bands = Hi / TR, units = B * bands;
-  const int rowv = Wi * RW;                    // values per input row
-  double acc = 0.0;
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int b = u / bands, y0 = (u - b * bands) * TR;   // input rows y0-1 .. y0+TR
-    __syncthreads();                            // the previous band's readers are done
-    for (int i = threadIdx.x * 4; i < (TR + 2) * rowv; i += blockDim.x * 4) {
-      const int rl = i / rowv, iy = y0 - 1 + rl;
-      f4 v = {{0.f, 0.f, 0.f, 0.f}};
-      if (iy >= 0 && iy < Hi) {
-        const unsigned off = (unsigned)((b * Hi + iy) * rowv + (i - rl * rowv));
-        const f4 a = ld_f4<T>(cg + off), s2 = ld_f4<T>(sg + off);
-#pragma unroll
-        for (int q = 0; q < 4; q++) v.v[q] = a.v[q] + s2.v[q];
-      }
-      *reinterpret_cast<float4*>(sv + i) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
-    }
-    __syncthreads();
-    const unsigned npx = 2u * TR * Wo;          // output pixels of the band
-    for (unsigned e = threadIdx.x; e < npx; e += blockDim.x) {
-      const unsigned ox = e % Wo, oyl = e / Wo, oy = 2u * y0 + oyl;
-      const int kh0 = (oy + 1) & 1, kw0 = (ox + 1) & 1;
-      float v[C];
-#pragma unroll
-      for (int c = 0; c < C; c++) v[c] = b0[c];
-#pragma unroll
-      for (int a = 0; a < 2; a++) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int kh = kh0 + 2 * a, kw = kw0 + 2 * q;
-          const int ty = (int)oy + 1 - kh, tx = (int)ox + 1 - kw;
-          const int iy = ty >> 1, ix = tx >> 1;
-          if (ty < 0 || iy >= Hi || tx < 0 || ix >= Wi) continue;
-          const float* sp = sv + ((iy - (y0 - 1)) * Wi + ix) * RW + (kh * 4 + kw) * C;
-#pragma unroll
-          for (int c = 0; c < C; c++) v[c] += sp[c];
-        }
-      }
-      const unsigned eo = (b * Ho + oy) * Wo + ox;
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        const float s = sigmoidf_(v[c]);
-        const float d = s - xt[eo * C + c];
-        acc += (double)d * (double)d;
-        st_f<T>(dg + eo * C + c, cf * 2.f * d * s * (1.f - s));
-      }
     }
   }
   __shared__ double sh[8];
@@ -263,29 +179,6 @@ int p2pvg_convt_c1_loss_impl(const void* col, const void* col2, int dtype, const
   P2PVG_REQUIRE(C == 1 || C == 3, P2PVG_ERR_UNSUPPORTED, "convt_c1_loss: 1 or 3 output channels (got %d)", C);
   P2PVG_REQUIRE((long long)B * Hi * Wi * 16 * C < (1LL << 31), P2PVG_ERR_UNSUPPORTED, "convt_c1_loss: group too large for 32-bit indexing");
   dim3 grid(MSE_CHUNKS, G);
-  // shared-memory-staged variant: 4-row bands of full image width (+ 2 halo rows) must fit the shared memory of a block
-  const size_t tile_bytes = (size_t)6 * Wi * 16 * C * sizeof(float);
-  static int tiled_env = -1;
-  if (tiled_env < 0) {
-    const char* e = getenv("P2PVG_C1LOSS_TILED");
-    tiled_env = e ? atoi(e) : 1;
-  }
-  if (tiled_env && Hi % 4 == 0 && tile_bytes <= 100 * 1024 && (Wi * 16 * C) % 4 == 0) {
-    static bool attr1 = false, attr3 = false;
-#define LT(T, CC, FLAG)                                                                                                              \
-    do {                                                                                                                              \
-      if (!FLAG) {                                                                                                                    \
-        cudaFuncSetAttribute(convt_c1_loss_tiled_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);             \
-      }                                                                                                                               \
-      convt_c1_loss_tiled_kernel<T, CC><<<grid, 256, tile_bytes, st>>>((const T*)col, (const T*)col2, grp_src, bias, x, tgt, coef, B, Hi, Wi, \
-                                                                      (T*)d_raw, partial);                                            \
-    } while (0)
-    if (dtype == P2PVG_BF16) {
-      if (C == 1) { LT(bf16, 1, attr1); attr1 = true; } else { LT(bf16, 3, attr3); attr3 = true; }
-      return p2pvg_check_launch("convt_c1_loss (tiled)");
-    }
-#undef LT
-  }
   if (C == 1) {
     DISPATCH_DTYPE(dtype, T, (convt_c1_loss_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)col, (const T*)col2, grp_src, bias, x, tgt, coef, B, Hi, Wi,
                                                                                (T*)d_raw, partial)));

@@ -390,7 +390,7 @@ def test_sigmoid_mse_finalize_adam(KS, dtype):
 @pytest.mark.parametrize("Hi", [8, 6, 32])
 def test_convt_c1_loss_equals_col2im_plus_sigmoid_mse(C, Hi):
     """Fused last decoder layer (tap gather + bias + sigmoid + MSE + d raw) against the two-kernel path it replaces.
-    Hi % 4 == 0 runs the shared-memory-staged variant (4-row bands), Hi = 6 the direct-gather one."""
+    Several image sizes (the gather handles the borders per pixel)."""
     from p2pvg_b200._lib import CudaKernels
     K = CudaKernels("cuda")
     torch.manual_seed(0)

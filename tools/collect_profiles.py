@@ -42,8 +42,8 @@ for n in (2, 8):
         last_json_line(os.path.relpath(f, G), f"bench_r02_N{n}_" + os.path.basename(f)[6:])
     cp(f"r2m{n}/dp_check.log", f"dp_check_r02_N{n}.txt")
 ab = []
-for d in ("r2c", "r2d", "r2e", "r2f", "r2g", "r2h", "r2i", "r2o"):
-    f = os.path.join(G, d, "ab.txt" if d < "r2h" else "scan.txt")
+for d in ("r2c", "r2d", "r2e", "r2f", "r2g", "r2h", "r2i", "r2o", "r2s"):
+    f = os.path.join(G, d, "scan.txt" if d in ("r2h", "r2i", "r2o") else "ab.txt")
     if os.path.exists(f):
         ab.append(f"##### job {d} (one box per job; compare lines within a job only)\n" + open(f).read())
 if ab:
