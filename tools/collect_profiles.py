@@ -49,10 +49,10 @@ for d in ("r2c", "r2d", "r2e", "r2f", "r2g", "r2h", "r2i", "r2o", "r2s"):
 if ab:
     open(os.path.join(P, "ab_r02.txt"), "w").write("\n".join(ab))
     print("ok   ab_r02.txt")
-cp("r2z/launches_C2.txt", "launches_r02_C2.txt")
+cp("r2r/launches_C2.txt", "launches_r02_C2.txt")
 cp("r2z/calls_C2.txt", "calls_r02_C2.txt")
 cp("r2p/calls_C2.txt", "calls_r02_C2_before_helper_kernel_fixes.txt")
-cp("r2f/calls_C3.txt", "calls_r02_C3.txt")
+cp("r2r/calls_C3.txt", "calls_r02_C3.txt")
 cp("r2p/calls_C3.txt", "calls_r02_C3_before_vectorised_data_movement.txt")
 cp("r2p/scan_R512.txt", "scan_r02_R512_before_48_row_slabs.txt")
 cp("r2z/calls_C4.txt", "calls_r02_C4.txt")
