@@ -11,7 +11,7 @@ timeout 170 bash -c "$(declare -f run); N=$N; run bench.py --gpus $N --steps 20 
 if [ "$N" = "8" ]; then
   timeout 170 bash -c "$(declare -f run); N=$N; run bench.py --config C4 --gpus $N --steps 20 --warmup 5 --skip-cpu" > $O/bench_C4.json 2> $O/bench_C4.err; echo "bench C4 rc=$?" >> $O/rc.txt
   timeout 170 bash -c "$(declare -f run); N=$N; run bench.py --config C5 --gpus $N --steps 20 --warmup 5 --skip-cpu" > $O/bench_C5.json 2> $O/bench_C5.err; echo "bench C5 rc=$?" >> $O/rc.txt
-  [ -n "$MGPU_MODE_B" ] && P2PVG_UPDATE_MODE=B timeout 170 bash -c "$(declare -f run); N=$N; run bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu" > $O/bench_C2_weak_modeB.json 2> $O/bench_C2_weak_modeB.err; echo "bench C2 mode B rc=$?" >> $O/rc.txt
+  [ -z "$MGPU_MODE_B" ] || P2PVG_UPDATE_MODE=B timeout 170 bash -c "$(declare -f run); N=$N; run bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu" > $O/bench_C2_weak_modeB.json 2> $O/bench_C2_weak_modeB.err; echo "bench C2 mode B rc=$?" >> $O/rc.txt
 fi
 cat $O/rc.txt
 for f in $O/bench_*.json; do echo $f; python - "$f" <<'PY'
