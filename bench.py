@@ -379,7 +379,9 @@ def main():
         call(xb)
     barrier()
     e0.record()
-    pf = DevicePrefetcher(host_batches(args.steps), dev, early_release=True,   # one train step per batch, nothing else reads it
+    # one train step per batch, nothing else reads it -> the slot may be refilled as soon as the step has copied it away; with
+    # several GPUs the refill is left where it was (after the step = during the next forward), away from the all-reduce phases
+    pf = DevicePrefetcher(host_batches(args.steps), dev, early_release=(world == 1),
                           copy_streams=int(os.environ.get("P2PVG_BENCH_COPY_STREAMS", "1")))
     for xb in pf:
         losses = call(xb)
