@@ -90,3 +90,31 @@ def test_scan512_slab_size_invariance(K):
         part = run(rows)
         for a, b, nm in zip(full, part, ("gates", "h", "c")):
             assert torch.equal(a[:, rows], b), f"{nm}: rows {rows[0]}..{rows[-1]} depend on the slab size"
+
+
+def test_scan512_backward_slab_size_invariance(K):
+    """The R=512 backward scan has two implementations: 16-row slabs with the non-register weight half in shared memory, and
+    32 / 48-row slabs with that half in tensor memory (tcgen05.st / tcgen05.ld).  Per batch row the arithmetic is the same
+    (same k order, the 16 partial products summed in rank order), so the gradients of rows taken from a 256-row launch
+    (48-row slabs) and from a 128-row launch (32-row slabs) must be bit-identical to those rows launched alone (16-row slabs)."""
+    S, R = 5, 512
+    torch.manual_seed(4)
+    dev = "cuda"
+    Bf = 256
+    whh = torch.randn(4 * R, R, device=dev) * (1.0 / R ** 0.5)
+    gates = torch.rand(S, Bf, 4 * R, device=dev) * 0.8 + 0.1
+    gates[:, :, 2 * R:3 * R] = gates[:, :, 2 * R:3 * R] * 2 - 1          # the g gate is a tanh
+    cs = torch.randn(S + 1, Bf, R, device=dev) * 0.5
+    dh = torch.randn(S, Bf, R, device=dev)
+
+    def run(rows):
+        B = len(rows)
+        dG = torch.empty(S, B, 4 * R, device=dev)
+        ctr = torch.zeros(4, dtype=torch.int32, device=dev)
+        K.lstm_scan_bwd(dh[:, rows].contiguous(), whh, gates[:, rows].contiguous(), cs[:, rows].contiguous(), dG, S, B, R, ctr, tf32=True)
+        return dG
+
+    full = run(list(range(Bf)))                       # 6 clusters of 48 rows
+    for rows in (list(range(40)), list(range(200, 256)), list(range(64, 192))):   # 16-row slabs, 16-row slabs, 32-row slabs
+        part = run(rows)
+        assert torch.equal(full[:, rows], part), f"rows {rows[0]}..{rows[-1]} depend on the slab size"
