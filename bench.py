@@ -375,16 +375,23 @@ def main():
     def call(xb):
         return model((None, xb, None), 0, T - 1) if pose else model(xb, 0, T - 1)
 
-    for xb in DevicePrefetcher(host_batches(2), dev):
-        call(xb)
+    # ONE input pipeline for warm-up and timed steps, so that the timed region sees its steady state (no stream / slot set-up, no
+    # un-overlapped first copy): 3 warm-up steps, then exactly K steps, each of which issues the host->device copy of a following
+    # batch (one batch more than consumed is supplied, so the last timed step does too -> K copies of h2d_bytes_per_step inside
+    # the region).  One train step per batch, nothing else reads it -> the slot may be refilled as soon as the step has copied it
+    # away; with several GPUs the refill is left where it was (after the step = during the next forward), away from the
+    # all-reduce phases.
+    e2e_warm = 3
+    pf = DevicePrefetcher(host_batches(e2e_warm + args.steps + 1), dev, early_release=(world == 1),
+                          copy_streams=int(os.environ.get("P2PVG_BENCH_COPY_STREAMS", "1")))
+    feed = iter(pf)
+    for _ in range(e2e_warm):
+        call(next(feed))
+        pf.release()
     barrier()
     e0.record()
-    # one train step per batch, nothing else reads it -> the slot may be refilled as soon as the step has copied it away; with
-    # several GPUs the refill is left where it was (after the step = during the next forward), away from the all-reduce phases
-    pf = DevicePrefetcher(host_batches(args.steps), dev, early_release=(world == 1),
-                          copy_streams=int(os.environ.get("P2PVG_BENCH_COPY_STREAMS", "1")))
-    for xb in pf:
-        losses = call(xb)
+    for _ in range(args.steps):
+        losses = call(next(feed))
         pf.release()
     e1.record()
     barrier()
