@@ -199,18 +199,24 @@ int p2pvg_bn_ema(float* rmean, float* rvar, const float* mean, const float* var_
 int p2pvg_lstm_pointwise_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, int B, int R, void* stream);
 int p2pvg_lstm_pointwise_bwd(const float* dh, const float* dc_next, const float* gates, const float* c_prev, const float* c,
                              float* dgates, float* dc_prev, int B, int R, void* stream);
-/* Whole-sequence recurrence of one nn.LSTMCell layer in ONE persistent cooperative launch (grid barrier per timestep):
+/* Whole-sequence recurrence of one nn.LSTMCell layer in ONE persistent launch (the W_hh slice of a CTA stays on chip for all
+ * timesteps).  tf32 = 1 dispatches by hidden size: R in {64,128,256}: thread-block clusters of 8 CTAs, hardware cluster barrier per
+ * timestep; R = 512: clusters of 16 CTAs (non-portable size), slabs of 16 / 32 / 48 batch rows per cluster chosen so that the
+ * resident clusters cover the batch in one wave, backward reduction scattered through distributed shared memory, the part of the
+ * weight slice that does not fit the registers in shared memory (16-row slabs) or tensor memory (larger slabs).  tf32 = 0 (and
+ * P2PVG_LSTM_CLUSTER=0): cooperative grid with a grid barrier per timestep, exact fp32 FFMA products.
  *   forward : gates_s = pre_s + b_hh + h_{s-1}.W_hh^T -> (i,f,g,o) -> c_s, h_s       pre [S,B,4R] = x-part incl. b_ih
  *             gates [S,B,4R] out (activations), hs / cs [S+1,B,R] with slot 0 = initial state (zeros, models/lstm.py:21-27)
  *   backward: dh_s = dhtop_s + dG_{s+1}.W_hh, cell backward -> dG [S,B,4R] (gradient w.r.t. the gate pre-activations)
- * `counter` is a zero-initialised uint32 in device memory (the grid barrier); R %% 64 == 0, R <= 256.
- * tf32 = 0: exact fp32 FFMA products (parity mode); tf32 = 1: the recurrent products on the tensor cores (mma.sync tf32). */
+ * `counter` is a zero-initialised uint32 in device memory (the grid barrier of the cooperative variant); R %% 64 == 0, R <= 256, or
+ * R = 512 (tf32 = 1: any batch; tf32 = 0: as long as the cooperative grid fits).  Unsupported shapes return P2PVG_ERR_UNSUPPORTED.
+ * tf32 = 1: the recurrent products on the tensor cores (mma.sync m16n8k8 tf32, fp32 accumulation). */
 int p2pvg_lstm_scan_fwd(const float* pre, const float* whh, const float* bhh, float* gates, float* hs, float* cs, int S, int B, int R,
                         int tf32, unsigned* counter, void* stream);
 int p2pvg_lstm_scan_bwd(const float* dhtop, const float* whh, const float* gates, const float* cs, float* dG, int S, int B, int R,
                         int tf32, unsigned* counter, void* stream);
-/* diagnostics: cudaOccupancyMaxActiveClusters of the hidden-size-512 scans (clusters of 16 CTAs): which = 0 forward (16-row
- * slabs), 1 forward (32-row slabs), 2 backward; -1 on error */
+/* diagnostics: cudaOccupancyMaxActiveClusters of the hidden-size-512 scans (clusters of 16 CTAs): which = 0 / 1 / 3 forward with
+ * 16- / 32- / 48-row slabs, 2 / 4 / 5 backward with 16- / 32- / 48-row slabs; -1 on error */
 int p2pvg_lstm_cluster512_max_clusters(int which);
 /* the same for the hidden-size-256 scans (clusters of 8 CTAs): which = 0 / 1 forward with 16- / 32-row slabs, 2 / 3 backward */
 int p2pvg_lstm_cluster_max_clusters(int which);
